@@ -1,0 +1,539 @@
+// kmap.cu -- kernel-map construction, CSR view, lookups and target-topology candidate emission.
+//
+// Replaces GatherScatterDefault.cu:92-294 (two full sweeps with one un-cached root-to-leaf walk per
+// (voxel, tap) probe and K^3 contended global counters).  Here one CTA owns one *output leaf*: its
+// lanes walk the tree once per source leaf of the probe neighbourhood (<= 3x3x3 leaves for every
+// K <= 9 stride-1 kernel), stage those leaves' mask / prefix / base lines in shared memory with
+// 16-byte loads, and answer all voxel x tap probes from shared memory.  The map is written tap-major
+// so that consecutive rows of a leaf store coalesced.
+#include "fvc_common.cuh"
+
+#include <cub/cub.cuh>
+
+namespace fvc {
+
+constexpr int KM_THREADS = 128;
+constexpr int KM_MAX_NB = 128;    // cached source leaves per output leaf
+constexpr int KM_MAX_TAPS = 1024; // taps with shared-memory tap table / counters
+
+struct LeafBox {
+    int lmin[3];
+    int n[3];
+    int total;
+};
+
+// Source-leaf box reached from the output leaf at `origin` (ConvolutionGeometry.h:99-124 applied to
+// the two corners of the leaf).
+__device__ __forceinline__ LeafBox probe_box(const Geometry &g, const int origin[3], int transposed) {
+    LeafBox box;
+    box.total = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int lo, hi;
+        if (!transposed) {
+            lo = g.s[d] * origin[d] - g.pad[d];
+            hi = g.s[d] * (origin[d] + 7) + g.k[d] - 1 - g.pad[d];
+        } else {
+            lo = floor_div(origin[d] - (g.k[d] - 1 - g.pad[d]), g.s[d]);
+            hi = floor_div(origin[d] + 7 + g.pad[d], g.s[d]);
+        }
+        box.lmin[d] = lo >> 3;
+        box.n[d] = (hi >> 3) - (lo >> 3) + 1;
+        // saturate so that the product cannot overflow
+        box.total = (box.total > KM_MAX_NB || box.n[d] > KM_MAX_NB) ? KM_MAX_NB + 1 : box.total * box.n[d];
+    }
+    return box;
+}
+
+__global__ void __launch_bounds__(KM_THREADS)
+kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transposed, int32_t *__restrict__ nbr,
+                  int64_t pitch, unsigned long long *__restrict__ tap_counts) {
+    __shared__ __align__(16) uint64_t s_mask[KM_MAX_NB][8];
+    __shared__ __align__(16) uint16_t s_prefix[KM_MAX_NB][8];
+    __shared__ int s_base[KM_MAX_NB];
+    __shared__ int s_leaf[KM_MAX_NB];
+    __shared__ uint16_t s_vox[512];
+    __shared__ uint32_t s_tap[KM_MAX_TAPS];
+    __shared__ uint32_t s_cnt[KM_MAX_TAPS];
+
+    const int tid = threadIdx.x;
+    const FvcLeaf *L = out.leaves + blockIdx.x;
+    const int b = __ldg(&L->batch);
+    const int origin[3] = {__ldg(&L->origin[0]), __ldg(&L->origin[1]), __ldg(&L->origin[2])};
+    const int base = __ldg(&L->base);
+    const int cnt = __ldg(&L->count);
+    const int k3 = int(g.volume);
+    const bool small_taps = k3 <= KM_MAX_TAPS;
+    const int k12 = g.k[1] * g.k[2];
+
+    const LeafBox box = probe_box(g, origin, transposed);
+    const bool cached = box.total <= KM_MAX_NB;
+
+    // (1) lanes walk the tree in parallel, one source leaf each
+    if (cached) {
+        for (int t = tid; t < box.total; t += KM_THREADS) {
+            const int c = t % box.n[2], bb = (t / box.n[2]) % box.n[1], a = t / (box.n[2] * box.n[1]);
+            const int leaf = find_leaf(feat, b, (box.lmin[0] + a) << 3, (box.lmin[1] + bb) << 3, (box.lmin[2] + c) << 3);
+            s_leaf[t] = leaf;
+            s_base[t] = leaf >= 0 ? __ldg(&feat.leaves[leaf].base) : 0;
+        }
+    }
+    if (small_taps) {
+        for (int k = tid; k < k3; k += KM_THREADS) {
+            s_tap[k] = (uint32_t(k / k12) << 20) | (uint32_t((k / g.k[2]) % g.k[1]) << 10) | uint32_t(k % g.k[2]);
+            s_cnt[k] = 0;
+        }
+    }
+    // (2) compact the output leaf's active voxels: rank inside the leaf == row - base
+    for (int n = tid; n < 512; n += KM_THREADS) {
+        const int w = n >> 6, bit = n & 63;
+        const uint64_t m = __ldg(L->mask + w);
+        if ((m >> bit) & 1ull)
+            s_vox[int(__ldg(L->prefix + w)) + __popcll(m & ((1ull << bit) - 1ull))] = uint16_t(n);
+    }
+    __syncthreads();
+    // (3) stage mask (4 x 16 B) + prefix (1 x 16 B) of every source leaf
+    if (cached) {
+        for (int e = tid; e < box.total * 5; e += KM_THREADS) {
+            const int li = e / 5, part = e % 5, leaf = s_leaf[li];
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (leaf >= 0)
+                v = __ldg(reinterpret_cast<const uint4 *>(feat.leaves + leaf) + part);
+            if (part < 4)
+                reinterpret_cast<uint4 *>(&s_mask[li][0])[part] = v;
+            else
+                *reinterpret_cast<uint4 *>(&s_prefix[li][0]) = v;
+        }
+    }
+    __syncthreads();
+
+    // (4) all voxel x tap probes; j (voxel) is the fastest index so stores to nbr[k][base + j] coalesce
+    const uint32_t items = uint32_t(cnt) * uint32_t(k3);
+    for (uint32_t item = tid; item < items; item += KM_THREADS) {
+        const int k = int(item / uint32_t(cnt)), j = int(item - uint32_t(k) * uint32_t(cnt));
+        const int n = s_vox[j];
+        const int c[3] = {origin[0] + (n >> 6), origin[1] + ((n >> 3) & 7), origin[2] + (n & 7)};
+        int t[3];
+        if (small_taps) {
+            const uint32_t packed = s_tap[k];
+            t[0] = int(packed >> 20), t[1] = int((packed >> 10) & 1023), t[2] = int(packed & 1023);
+        } else {
+            t[0] = k / k12, t[1] = (k / g.k[2]) % g.k[1], t[2] = k % g.k[2];
+        }
+        int p[3];
+        bool ok = true;
+        if (!transposed) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                p[d] = g.s[d] * c[d] + t[d] - g.pad[d]; // fineFromCoarse
+        } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { // coarseFromFine with the divisibility test
+                const int numer = c[d] - t[d] + g.pad[d];
+                ok = ok && floor_mod(numer, g.s[d]) == 0;
+                p[d] = floor_div(numer, g.s[d]);
+            }
+        }
+        int val = -1;
+        if (ok) {
+            if (cached) {
+                const int li = (((p[0] >> 3) - box.lmin[0]) * box.n[1] + ((p[1] >> 3) - box.lmin[1])) * box.n[2] +
+                               ((p[2] >> 3) - box.lmin[2]);
+                if (s_leaf[li] >= 0) {
+                    const int w = p[0] & 7;
+                    val = leaf_value(s_mask[li][w], s_prefix[li][w], s_base[li], p[1], p[2]);
+                }
+            } else {
+                val = lookup_row(feat, b, p[0], p[1], p[2]);
+            }
+        }
+        nbr[int64_t(k) * pitch + base + j] = val;
+        if (val >= 0) {
+            if (small_taps)
+                atomicAdd(&s_cnt[k], 1u);
+            else
+                atomicAdd(tap_counts + k, 1ull);
+        }
+    }
+    if (small_taps) {
+        __syncthreads();
+        for (int k = tid; k < k3; k += KM_THREADS)
+            if (s_cnt[k])
+                atomicAdd(tap_counts + k, (unsigned long long)s_cnt[k]);
+    }
+}
+
+// ---- CSR-by-tap view ------------------------------------------------------------------------------
+constexpr int CSR_THREADS = 256;
+constexpr int CSR_ROWS_PER_THREAD = 8;
+constexpr int CSR_ROWS = CSR_THREADS * CSR_ROWS_PER_THREAD;
+
+__global__ void __launch_bounds__(CSR_THREADS)
+csr_count_kernel(const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int64_t nblk,
+                 int64_t *__restrict__ counts) {
+    const int64_t k = blockIdx.y, blk = blockIdx.x;
+    const int64_t row0 = blk * CSR_ROWS + int64_t(threadIdx.x) * CSR_ROWS_PER_THREAD;
+    int local = 0;
+#pragma unroll
+    for (int r = 0; r < CSR_ROWS_PER_THREAD; ++r)
+        if (row0 + r < n_out)
+            local += nbr[k * pitch + row0 + r] >= 0;
+    using BlockReduce = cub::BlockReduce<int, CSR_THREADS>;
+    __shared__ typename BlockReduce::TempStorage temp;
+    const int total = BlockReduce(temp).Sum(local);
+    if (threadIdx.x == 0)
+        counts[k * nblk + blk] = total;
+}
+
+__global__ void __launch_bounds__(CSR_THREADS)
+csr_fill_kernel(const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int64_t nblk,
+                const int64_t *__restrict__ block_offsets, int32_t *__restrict__ gather, int32_t *__restrict__ scatter) {
+    const int64_t k = blockIdx.y, blk = blockIdx.x;
+    const int64_t row0 = blk * CSR_ROWS + int64_t(threadIdx.x) * CSR_ROWS_PER_THREAD;
+    int vals[CSR_ROWS_PER_THREAD];
+    int local = 0;
+#pragma unroll
+    for (int r = 0; r < CSR_ROWS_PER_THREAD; ++r) {
+        vals[r] = row0 + r < n_out ? nbr[k * pitch + row0 + r] : -1;
+        local += vals[r] >= 0;
+    }
+    using BlockScan = cub::BlockScan<int, CSR_THREADS>;
+    __shared__ typename BlockScan::TempStorage temp;
+    int rank;
+    BlockScan(temp).ExclusiveSum(local, rank);
+    int64_t pos = block_offsets[k * nblk + blk] + rank;
+#pragma unroll
+    for (int r = 0; r < CSR_ROWS_PER_THREAD; ++r)
+        if (vals[r] >= 0) {
+            gather[pos] = vals[r];
+            scatter[pos] = int32_t(row0 + r);
+            ++pos;
+        }
+}
+
+__global__ void csr_offsets_kernel(const int64_t *__restrict__ block_offsets, const int64_t *__restrict__ last_count,
+                                   int64_t nblk, int64_t k3, int64_t *__restrict__ offsets) {
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k < k3)
+        offsets[k] = block_offsets[k * nblk];
+    else if (k == k3)
+        offsets[k3] = k3 * nblk > 0 ? block_offsets[k3 * nblk - 1] + *last_count : 0;
+}
+
+__global__ void reverse_dense_kernel(const int32_t *__restrict__ gather, const int32_t *__restrict__ scatter,
+                                     const int64_t *__restrict__ offsets, int k3, int64_t total,
+                                     int32_t *__restrict__ nbr_rev, int64_t pitch_rev) {
+    for (int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; p < total; p += int64_t(gridDim.x) * blockDim.x) {
+        int lo = 0, hi = k3; // largest k with offsets[k] <= p
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(offsets + mid) <= p)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        nbr_rev[int64_t(lo) * pitch_rev + gather[p]] = scatter[p];
+    }
+}
+
+__global__ void degree_kernel(const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int k3,
+                              int32_t *__restrict__ degree) {
+    for (int64_t o = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; o < n_out; o += int64_t(gridDim.x) * blockDim.x) {
+        int d = 0;
+        for (int k = 0; k < k3; ++k)
+            d += nbr[int64_t(k) * pitch + o] >= 0;
+        degree[o] = d;
+    }
+}
+
+// ---- lookups --------------------------------------------------------------------------------------
+__global__ void neighbor_indexes_kernel(FvcGridBatch grid, const int32_t *__restrict__ q_ijk,
+                                        const int32_t *__restrict__ q_bidx, int64_t nq, int extent, int shift,
+                                        int64_t *__restrict__ out) {
+    const int w = 2 * extent + 1, w3 = w * w * w;
+    const int64_t total = nq * w3;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t q = i / w3;
+        const int o = int(i - q * w3);
+        const int b = q_bidx ? q_bidx[q] : 0;
+        const int x = (q_ijk[3 * q] << shift) + o / (w * w) - extent;
+        const int y = (q_ijk[3 * q + 1] << shift) + (o / w) % w - extent;
+        const int z = (q_ijk[3 * q + 2] << shift) + o % w - extent;
+        const int row = lookup_row(grid, b, x, y, z);
+        out[i] = row >= 0 ? int64_t(row) - __ldg(grid.voxel_offsets + b) : -1; // per-grid-local (NeighborIndexes.cu:40)
+    }
+}
+
+__global__ void ijk_to_index_kernel(FvcGridBatch grid, const int32_t *__restrict__ q_ijk,
+                                    const int32_t *__restrict__ q_bidx, int64_t nq, int cumulative,
+                                    int64_t *__restrict__ out) {
+    for (int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; q < nq; q += int64_t(gridDim.x) * blockDim.x) {
+        const int b = q_bidx ? q_bidx[q] : 0;
+        const int row = lookup_row(grid, b, q_ijk[3 * q], q_ijk[3 * q + 1], q_ijk[3 * q + 2]);
+        out[q] = row < 0 ? -1 : (cumulative ? int64_t(row) : int64_t(row) - __ldg(grid.voxel_offsets + b));
+    }
+}
+
+// ---- generated target topologies ------------------------------------------------------------------
+// number of taps t in [0, k) with (c - t + pad) divisible by s  == taps congruent to (c + pad) mod s
+__device__ __forceinline__ int divisible_taps(int c, int k, int s, int pad) {
+    const int r = floor_mod(c + pad, s);
+    return r < k ? (k - 1 - r) / s + 1 : 0;
+}
+
+__global__ void conv_grid_count_kernel(const int32_t *__restrict__ ijk, int64_t n, Geometry g,
+                                       unsigned long long *__restrict__ counter) {
+    unsigned long long local = 0;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        local += (unsigned long long)divisible_taps(ijk[3 * i], g.k[0], g.s[0], g.pad[0]) *
+                 divisible_taps(ijk[3 * i + 1], g.k[1], g.s[1], g.pad[1]) *
+                 divisible_taps(ijk[3 * i + 2], g.k[2], g.s[2], g.pad[2]);
+    }
+    using BlockReduce = cub::BlockReduce<unsigned long long, 256>;
+    __shared__ typename BlockReduce::TempStorage temp;
+    const unsigned long long total = BlockReduce(temp).Sum(local);
+    if (threadIdx.x == 0 && total)
+        atomicAdd(counter, total);
+}
+
+// forward: each fine voxel emits floorDiv(fine - tap + pad, S) for every divisible tap
+// (BuildGridForConv.cu:485-510); candidates are claimed with one atomic per voxel (order is irrelevant,
+// the grid builder sorts and de-duplicates).
+__global__ void conv_grid_emit_fwd_kernel(const int32_t *__restrict__ ijk, const int32_t *__restrict__ bidx, int64_t n,
+                                          Geometry g, int64_t capacity, int32_t *__restrict__ cand_ijk,
+                                          int32_t *__restrict__ cand_bidx, unsigned long long *__restrict__ counter) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const int c[3] = {ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]};
+        int r[3], m[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            r[d] = floor_mod(c[d] + g.pad[d], g.s[d]); // smallest admissible tap
+            m[d] = divisible_taps(c[d], g.k[d], g.s[d], g.pad[d]);
+        }
+        const int total = m[0] * m[1] * m[2];
+        if (total == 0)
+            continue;
+        int64_t pos = int64_t(atomicAdd(counter, (unsigned long long)total));
+        const int b = bidx ? bidx[i] : 0;
+        for (int a = 0; a < m[0]; ++a)
+            for (int bb = 0; bb < m[1]; ++bb)
+                for (int cc = 0; cc < m[2]; ++cc, ++pos) {
+                    if (pos >= capacity)
+                        return;
+                    cand_ijk[3 * pos] = floor_div(c[0] - (r[0] + a * g.s[0]) + g.pad[0], g.s[0]);
+                    cand_ijk[3 * pos + 1] = floor_div(c[1] - (r[1] + bb * g.s[1]) + g.pad[1], g.s[1]);
+                    cand_ijk[3 * pos + 2] = floor_div(c[2] - (r[2] + cc * g.s[2]) + g.pad[2], g.s[2]);
+                    cand_bidx[pos] = b;
+                }
+    }
+}
+
+// transposed: every coarse voxel spreads through every tap (BuildGridForConvTranspose.cu:326-337)
+__global__ void conv_grid_emit_tr_kernel(const int32_t *__restrict__ ijk, const int32_t *__restrict__ bidx, int64_t n,
+                                         Geometry g, int32_t *__restrict__ cand_ijk, int32_t *__restrict__ cand_bidx) {
+    const int64_t k3 = g.volume, total = n * k3;
+    const int k12 = g.k[1] * g.k[2];
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = e / k3;
+        const int k = int(e - i * k3);
+        cand_ijk[3 * e] = g.s[0] * ijk[3 * i] + k / k12 - g.pad[0];
+        cand_ijk[3 * e + 1] = g.s[1] * ijk[3 * i + 1] + (k / g.k[2]) % g.k[1] - g.pad[1];
+        cand_ijk[3 * e + 2] = g.s[2] * ijk[3 * i + 2] + k % g.k[2] - g.pad[2];
+        cand_bidx[e] = bidx ? bidx[i] : 0;
+    }
+}
+
+static inline int grid_for(int64_t n, int block) {
+    int64_t blocks = ceil_div(n, block);
+    return int(blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks));
+}
+
+static int check_geometry_args(const int32_t kernel_size[3], const int32_t stride[3]) {
+    for (int d = 0; d < 3; ++d) {
+        FVC_REQUIRE(kernel_size[d] > 0, FVC_ERR_RUNTIME, "kernel_size[%d] must be positive, got %d", d, kernel_size[d]);
+        FVC_REQUIRE(stride[d] > 0, FVC_ERR_RUNTIME, "stride[%d] must be positive, got %d", d, stride[d]);
+    }
+    return FVC_OK;
+}
+
+} // namespace fvc
+
+using namespace fvc;
+
+extern "C" {
+
+int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_grid, const int32_t kernel_size[3],
+                   const int32_t stride[3], int32_t transposed, int32_t *nbr, int64_t pitch, int64_t *tap_counts,
+                   fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(feature_grid && output_grid, FVC_ERR_RUNTIME, "feature_grid and output_grid must be provided");
+    int rc = check_geometry_args(kernel_size, stride); // GatherScatterDefault.cu:63-67
+    if (rc)
+        return rc;
+    FVC_REQUIRE(feature_grid->num_grids == output_grid->num_grids, FVC_ERR_RUNTIME,
+                "feature_grid and output_grid must have the same batch size, got %d and %d", feature_grid->num_grids,
+                output_grid->num_grids);
+    FVC_REQUIRE(feature_grid->total_voxels <= INT32_MAX, FVC_ERR_RUNTIME,
+                "feature_grid has %lld voxels, exceeding the int32 index limit (%d)",
+                (long long)feature_grid->total_voxels, INT32_MAX); // :68-74
+    FVC_REQUIRE(output_grid->total_voxels <= INT32_MAX, FVC_ERR_RUNTIME,
+                "output_grid has %lld voxels, exceeding the int32 index limit (%d)",
+                (long long)output_grid->total_voxels, INT32_MAX); // :75-80
+    const Geometry g = make_geometry(kernel_size, stride);
+    FVC_REQUIRE(g.volume <= INT32_MAX, FVC_ERR_RUNTIME, "kernel volume %lld exceeds INT32_MAX", (long long)g.volume);
+    FVC_REQUIRE(pitch >= output_grid->total_voxels, FVC_ERR_RUNTIME, "map pitch %lld < output voxels %lld",
+                (long long)pitch, (long long)output_grid->total_voxels);
+    FVC_CUDA(cudaMemsetAsync(tap_counts, 0, size_t(g.volume) * 8, stream));
+    if (output_grid->num_leaves == 0)
+        return FVC_OK;
+    kmap_build_kernel<<<output_grid->num_leaves, KM_THREADS, 0, stream>>>(
+        *feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, reinterpret_cast<unsigned long long *>(tap_counts));
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+size_t fvc_kmap_csr_scratch_bytes(int64_t n_out, int64_t kernel_volume) {
+    const int64_t nblk = ceil_div(n_out > 0 ? n_out : 1, CSR_ROWS);
+    const int64_t m = nblk * (kernel_volume > 0 ? kernel_volume : 1);
+    size_t temp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp, (int64_t *)nullptr, (int64_t *)nullptr, m);
+    return align_up(size_t(m) * 8, 256) + 256 + align_up(temp, 256);
+}
+
+int fvc_kmap_to_csr(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume,
+                    const int64_t *tap_counts, int64_t *offsets_dev, int32_t *gather, int32_t *scatter, void *scratch,
+                    size_t scratch_bytes, fvc_stream_t stream_) {
+    (void)tap_counts;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(kernel_volume >= 0 && kernel_volume <= 65535, FVC_ERR_UNSUPPORTED,
+                "kernel volume %lld exceeds the CSR builder limit 65535", (long long)kernel_volume);
+    if (n_out == 0 || kernel_volume == 0) {
+        FVC_CUDA(cudaMemsetAsync(offsets_dev, 0, size_t(kernel_volume + 1) * 8, stream));
+        return FVC_OK;
+    }
+    const int64_t nblk = ceil_div(n_out, CSR_ROWS), m = nblk * kernel_volume;
+    FVC_REQUIRE(scratch && scratch_bytes >= fvc_kmap_csr_scratch_bytes(n_out, kernel_volume), FVC_ERR_RUNTIME,
+                "CSR scratch too small");
+    int64_t *counts = reinterpret_cast<int64_t *>(scratch);
+    int64_t *last = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + align_up(size_t(m) * 8, 256));
+    void *temp = reinterpret_cast<char *>(last) + 256;
+    size_t temp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, counts, m);
+    dim3 grid((unsigned)nblk, (unsigned)kernel_volume);
+    csr_count_kernel<<<grid, CSR_THREADS, 0, stream>>>(nbr, pitch, n_out, nblk, counts);
+    FVC_LAUNCH_CHECK();
+    FVC_CUDA(cudaMemcpyAsync(last, counts + (m - 1), 8, cudaMemcpyDeviceToDevice, stream));
+    FVC_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, counts, m, stream));
+    g_launch_count.fetch_add(1);
+    csr_offsets_kernel<<<int(ceil_div(kernel_volume + 1, 256)), 256, 0, stream>>>(counts, last, nblk, kernel_volume,
+                                                                                   offsets_dev);
+    FVC_LAUNCH_CHECK();
+    csr_fill_kernel<<<grid, CSR_THREADS, 0, stream>>>(nbr, pitch, n_out, nblk, counts, gather, scatter);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_kmap_reverse_dense(const int32_t *gather, const int32_t *scatter, const int64_t *offsets_dev,
+                           int64_t kernel_volume, int64_t total_pairs, int64_t n_feature, int32_t *nbr_rev,
+                           int64_t pitch_rev, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(pitch_rev >= n_feature, FVC_ERR_RUNTIME, "reverse map pitch %lld < feature voxels %lld",
+                (long long)pitch_rev, (long long)n_feature);
+    if (kernel_volume == 0 || pitch_rev == 0)
+        return FVC_OK;
+    FVC_CUDA(cudaMemsetAsync(nbr_rev, 0xFF, size_t(kernel_volume) * size_t(pitch_rev) * 4, stream));
+    if (total_pairs == 0)
+        return FVC_OK;
+    reverse_dense_kernel<<<grid_for(total_pairs, 256), 256, 0, stream>>>(gather, scatter, offsets_dev, int(kernel_volume),
+                                                                         total_pairs, nbr_rev, pitch_rev);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_kmap_degree(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, int32_t *degree,
+                    fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_out == 0)
+        return FVC_OK;
+    degree_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, pitch, n_out, int(kernel_volume), degree);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_neighbor_indexes(const FvcGridBatch *grid, const int32_t *query_ijk, const int32_t *query_bidx, int64_t nq,
+                         int32_t extent, int32_t shift, int64_t *out, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(grid, FVC_ERR_RUNTIME, "grid must be provided");
+    FVC_REQUIRE(extent >= 0, FVC_ERR_VALUE, "extent must be >= 0");
+    FVC_REQUIRE(shift >= 0 && shift < 31, FVC_ERR_VALUE, "bitshift must be in [0, 31)");
+    if (nq == 0)
+        return FVC_OK;
+    const int64_t w = 2 * extent + 1;
+    neighbor_indexes_kernel<<<grid_for(nq * w * w * w, 256), 256, 0, stream>>>(*grid, query_ijk, query_bidx, nq, extent,
+                                                                              shift, out);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_ijk_to_index(const FvcGridBatch *grid, const int32_t *query_ijk, const int32_t *query_bidx, int64_t nq,
+                     int32_t cumulative, int64_t *out, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(grid, FVC_ERR_RUNTIME, "grid must be provided");
+    if (nq == 0)
+        return FVC_OK;
+    ijk_to_index_kernel<<<grid_for(nq, 256), 256, 0, stream>>>(*grid, query_ijk, query_bidx, nq, cumulative, out);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_conv_grid_count(const int32_t *src_ijk, int64_t n, const int32_t kernel_size[3], const int32_t stride[3],
+                        int32_t transposed, void *scratch8, int64_t *count_host, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    int rc = check_geometry_args(kernel_size, stride);
+    if (rc)
+        return rc;
+    const Geometry g = make_geometry(kernel_size, stride);
+    FVC_REQUIRE(g.volume <= INT32_MAX, FVC_ERR_RUNTIME, "kernel volume %lld exceeds INT32_MAX (BuildGridForConv.cu:151-152)",
+                (long long)g.volume);
+    *count_host = 0;
+    if (n == 0)
+        return FVC_OK;
+    if (transposed) {
+        *count_host = n * g.volume;
+        return FVC_OK;
+    }
+    FVC_CUDA(cudaMemsetAsync(scratch8, 0, 8, stream));
+    conv_grid_count_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src_ijk, n, g,
+                                                                 reinterpret_cast<unsigned long long *>(scratch8));
+    FVC_LAUNCH_CHECK();
+    unsigned long long total = 0;
+    FVC_CUDA(cudaMemcpyAsync(&total, scratch8, 8, cudaMemcpyDeviceToHost, stream));
+    FVC_CUDA(cudaStreamSynchronize(stream));
+    *count_host = int64_t(total);
+    return FVC_OK;
+}
+
+int fvc_conv_grid_emit(const int32_t *src_ijk, const int32_t *src_bidx, int64_t n, const int32_t kernel_size[3],
+                       const int32_t stride[3], int32_t transposed, int64_t count, int32_t *cand_ijk,
+                       int32_t *cand_bidx, void *counter8, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    int rc = check_geometry_args(kernel_size, stride);
+    if (rc)
+        return rc;
+    const Geometry g = make_geometry(kernel_size, stride);
+    if (n == 0 || count == 0)
+        return FVC_OK;
+    if (transposed) {
+        FVC_REQUIRE(count == n * g.volume, FVC_ERR_RUNTIME, "transposed candidate count mismatch");
+        conv_grid_emit_tr_kernel<<<grid_for(count, 256), 256, 0, stream>>>(src_ijk, src_bidx, n, g, cand_ijk, cand_bidx);
+        FVC_LAUNCH_CHECK();
+        return FVC_OK;
+    }
+    FVC_CUDA(cudaMemsetAsync(counter8, 0, 8, stream));
+    conv_grid_emit_fwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src_ijk, src_bidx, n, g, count, cand_ijk, cand_bidx,
+                                                                   reinterpret_cast<unsigned long long *>(counter8));
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+} // extern "C"

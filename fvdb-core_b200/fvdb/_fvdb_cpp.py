@@ -1,0 +1,513 @@
+"""Drop-in for the convolution section of the reference's pybind11 module ``fvdb._fvdb_cpp``.
+
+Same names, argument meaning and error behaviour as src/python/Bindings.cpp:491-674 and
+src/python/GridBatchOps.cpp:764-792, implemented over the C ABI of libfvdbconv.so (include/fvdbconv.h).
+PyTorch is used for device memory and streams only; every computation is a hand-written sm_100a kernel
+reached through ``ctypes``.  There is no CPU path: CPU tensors are rejected.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, i3
+
+_DTYPE_CODE = {torch.float16: _lib.FVC_F16, torch.bfloat16: _lib.FVC_BF16, torch.float32: _lib.FVC_F32, torch.float64: _lib.FVC_F64}
+_INT32_MAX = 2**31 - 1
+
+# Executor variant forced by tests / bench ("auto" | "simt" | "tc"); the default picks per dtype / channels.
+_FORCED_PATH = {"auto": 0, "simt": 1, "tc": 2}
+_path = 0
+
+
+def set_conv_path(name: str) -> None:
+    """Force the CUDA-core ("simt") or tcgen05 ("tc") kernel family, or "auto" (default)."""
+    global _path
+    _path = _FORCED_PATH[name]
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: "torch.Tensor | None") -> int:
+    return 0 if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _require_cuda(device: torch.device, what: str) -> None:
+    if device.type != "cuda":
+        raise RuntimeError(
+            f"{what}: this build executes the ConvolutionPlan path on CUDA (sm_100a) only and has no CPU fallback; got device {device}"
+        )
+
+
+def _vec3(value) -> list[int]:
+    if isinstance(value, torch.Tensor):
+        value = value.tolist()
+    value = [int(v) for v in value]
+    if len(value) != 3:
+        raise ValueError(f"expected three values, got {value}")
+    return value
+
+
+# ---------------------------------------------------------------------------------------------
+# ConvolutionGeometry (Bindings.cpp:497-540 over ConvolutionGeometry.h)
+# ---------------------------------------------------------------------------------------------
+
+
+class ConvolutionGeometry:
+    """Immutable canonical geometry ``fine = stride * coarse + tap - padding_before``."""
+
+    def __init__(self, kernel_size, stride):
+        ks, st = _vec3(kernel_size), _vec3(stride)
+        before, after, volume = i3([0, 0, 0]), i3([0, 0, 0]), C.c_int64(0)
+        check(lib.fvc_geometry(i3(ks), i3(st), before, after, C.byref(volume)))
+        self._kernel_size, self._stride = ks, st
+        self._padding_before, self._padding_after = list(before), list(after)
+        self._kernel_volume = int(volume.value)
+
+    kernel_size = property(lambda self: list(self._kernel_size))
+    stride = property(lambda self: list(self._stride))
+    dilation = property(lambda self: [1, 1, 1])
+    padding_before = property(lambda self: list(self._padding_before))
+    padding_after = property(lambda self: list(self._padding_after))
+    registration_offset = property(lambda self: [0, 0, 0])
+    semantics_version = property(lambda self: 1)
+    kernel_volume = property(lambda self: self._kernel_volume)
+    phase_policy = property(lambda self: "torch_same_phase")
+
+    def tap_coord(self, tap_index: int) -> list[int]:
+        out = i3([0, 0, 0])
+        check(lib.fvc_geometry_tap_coord(i3(self._kernel_size), int(tap_index), out))
+        return list(out)
+
+    def fine_from_coarse(self, coarse, tap) -> list[int]:
+        out = i3([0, 0, 0])
+        check(lib.fvc_geometry_fine_from_coarse(i3(self._kernel_size), i3(self._stride), i3(coarse), i3(tap), out))
+        return list(out)
+
+    def coarse_from_fine(self, fine, tap) -> "list[int] | None":
+        out, ok = i3([0, 0, 0]), C.c_int32(0)
+        check(lib.fvc_geometry_coarse_from_fine(i3(self._kernel_size), i3(self._stride), i3(fine), i3(tap), out, C.byref(ok)))
+        return list(out) if ok.value else None
+
+
+# ---------------------------------------------------------------------------------------------
+# GridBatchData: the batched index grid (src/fvdb/GridBatchData.h:29-55) as torch-owned device arrays
+# ---------------------------------------------------------------------------------------------
+
+
+class GridBatchData:
+    """Device index grid + per-grid metadata.  Identity (``is_same``) is object identity, as in the
+    reference (src/python/GridBatchDataBinding.cpp:62-67)."""
+
+    def __init__(self, *, device, num_grids, counts, leaves, lower, upper, root_keys, root_offsets, voxel_offsets, leaf_offsets, ijk, jidx, voxel_sizes, origins):
+        self.device = torch.device(device)
+        self.num_grids = int(num_grids)
+        self.total_voxels, self.num_leaves, self.num_lower, self.num_upper = (int(c) for c in counts)
+        self.leaves, self.lower, self.upper, self.root_keys = leaves, lower, upper, root_keys
+        self.root_offsets, self.voxel_offsets, self.leaf_offsets = root_offsets, voxel_offsets, leaf_offsets
+        self.ijk, self.jidx = ijk, jidx
+        self.voxel_sizes = voxel_sizes  # float64 [B, 3], host (authoritative, GridBatchData.h:29-55)
+        self.origins = origins  # float64 [B, 3], host
+        self._struct = _lib.FvcGridBatch(
+            self.num_grids, self.num_leaves, self.num_lower, self.num_upper, self.total_voxels,
+            _ptr(leaves), _ptr(lower), _ptr(upper), _ptr(root_keys), root_offsets.data_ptr(), voxel_offsets.data_ptr(), leaf_offsets.data_ptr(),
+        )
+
+    @property
+    def struct(self):
+        return C.byref(self._struct)
+
+    @property
+    def grid_count(self) -> int:
+        return self.num_grids
+
+    def is_same(self, other: "GridBatchData") -> bool:
+        return self is other
+
+
+def _as_i32_coords(ijk: torch.Tensor) -> torch.Tensor:
+    if ijk.dtype.is_floating_point or ijk.dtype == torch.bool:
+        raise TypeError("ijk must have an integer type")
+    if ijk.ndim != 2 or ijk.shape[1] != 3:
+        raise ValueError(f"ijk must have shape (n, 3), got {tuple(ijk.shape)}")
+    return ijk.to(torch.int32).contiguous()
+
+
+def build_grid_from_ijk(ijk: torch.Tensor, jidx: "torch.Tensor | None", num_grids: int, voxel_sizes: torch.Tensor, origins: torch.Tensor) -> GridBatchData:
+    """(grid, ijk) rows -> index grid (replaces ops/BuildGridFromIjk.cu:52-111).  Duplicates and negative
+    coordinates are fine; one batched device pass + one count read-back."""
+    device = ijk.device
+    _require_cuda(device, "GridBatch construction")
+    if num_grids > 1024:
+        raise RuntimeError(f"batch size {num_grids} exceeds the 1024-grid limit")
+    ijk = _as_i32_coords(ijk)
+    n = int(ijk.shape[0])
+    bidx = None
+    if jidx is not None and num_grids > 1:
+        bidx = jidx.to(device=device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(device):
+        stream = _stream(device)
+        scratch_bytes = int(lib.fvc_grid_build_scratch_bytes(n))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device)
+        counts = (C.c_int64 * 4)()
+        check(lib.fvc_grid_build_count(_ptr(ijk), _ptr(bidx), n, num_grids, scratch.data_ptr(), scratch_bytes, C.byref(counts), stream))
+        nv, nl, nlow, nup = (int(c) for c in counts)
+        leaves = torch.empty(nl * 128, dtype=torch.uint8, device=device)
+        lower = torch.empty((nlow, 4096), dtype=torch.int32, device=device)
+        upper = torch.empty((nup, 32768), dtype=torch.int32, device=device)
+        root_keys = torch.empty((nup, 4), dtype=torch.int32, device=device)
+        root_offsets = torch.empty(num_grids + 1, dtype=torch.int32, device=device)
+        voxel_offsets = torch.empty(num_grids + 1, dtype=torch.int64, device=device)
+        leaf_offsets = torch.empty(num_grids + 1, dtype=torch.int32, device=device)
+        out_ijk = torch.empty((nv, 3), dtype=torch.int32, device=device)
+        out_jidx = torch.empty(nv, dtype=torch.int32, device=device)
+        check(
+            lib.fvc_grid_build_fill(
+                _ptr(ijk), _ptr(bidx), n, num_grids, scratch.data_ptr(), scratch_bytes, C.byref(counts),
+                _ptr(leaves), _ptr(lower), _ptr(upper), _ptr(root_keys), root_offsets.data_ptr(), voxel_offsets.data_ptr(),
+                leaf_offsets.data_ptr(), _ptr(out_ijk), _ptr(out_jidx), stream,
+            )
+        )
+    return GridBatchData(
+        device=device, num_grids=num_grids, counts=(nv, nl, nlow, nup), leaves=leaves, lower=lower, upper=upper, root_keys=root_keys,
+        root_offsets=root_offsets, voxel_offsets=voxel_offsets, leaf_offsets=leaf_offsets, ijk=out_ijk, jidx=out_jidx,
+        voxel_sizes=voxel_sizes, origins=origins,
+    )
+
+
+def _generated_grid(grid: GridBatchData, kernel_size, stride, transposed: bool) -> GridBatchData:
+    ks, st = _vec3(kernel_size), _vec3(stride)
+    ConvolutionGeometry(ks, st)  # validation (ValueError on non-positive sizes)
+    device = grid.device
+    _require_cuda(device, "conv_grid")
+    scale = torch.tensor(st, dtype=torch.float64)
+    voxel_sizes = grid.voxel_sizes / scale if transposed else grid.voxel_sizes * scale  # BuildGridForConv.cu:533-538, Transpose :350-355
+    with torch.cuda.device(device):
+        stream = _stream(device)
+        n = grid.total_voxels
+        counter = torch.zeros(2, dtype=torch.int64, device=device)
+        count = C.c_int64(0)
+        check(lib.fvc_conv_grid_count(_ptr(grid.ijk), n, i3(ks), i3(st), int(transposed), counter.data_ptr(), C.byref(count), stream))
+        m = int(count.value)
+        if m > _INT32_MAX:
+            raise RuntimeError(
+                f"generated topology would stage {m} candidate coordinates ({n} input voxels * {ks[0] * ks[1] * ks[2]} kernel taps), "
+                "exceeding the int32 limit; provide an explicit target grid"
+            )
+        cand_ijk = torch.empty((m, 3), dtype=torch.int32, device=device)
+        cand_bidx = torch.empty(m, dtype=torch.int32, device=device)
+        check(
+            lib.fvc_conv_grid_emit(
+                _ptr(grid.ijk), _ptr(grid.jidx), n, i3(ks), i3(st), int(transposed), m, _ptr(cand_ijk), _ptr(cand_bidx), counter.data_ptr() + 8, stream
+            )
+        )
+    return build_grid_from_ijk(cand_ijk, cand_bidx, grid.num_grids, voxel_sizes, grid.origins.clone())
+
+
+def conv_grid(grid: GridBatchData, kernel_size: Sequence[int], stride: Sequence[int]) -> GridBatchData:
+    """Complete forward support (GridBatchOps.cpp:764-776 -> ops::buildGridForConv)."""
+    return _generated_grid(grid, kernel_size, stride, transposed=False)
+
+
+def conv_transpose_grid(grid: GridBatchData, kernel_size: Sequence[int], stride: Sequence[int]) -> GridBatchData:
+    """Complete transposed support (GridBatchOps.cpp:778-792 -> ops::buildGridForConvTranspose)."""
+    return _generated_grid(grid, kernel_size, stride, transposed=True)
+
+
+def neighbor_indexes(grid: GridBatchData, ijk: torch.Tensor, jidx: "torch.Tensor | None", extent: int, bitshift: int = 0) -> torch.Tensor:
+    _require_cuda(grid.device, "neighbor_indexes")
+    ijk = _as_i32_coords(ijk.to(grid.device))
+    nq, w = int(ijk.shape[0]), 2 * int(extent) + 1
+    bidx = None if jidx is None or grid.num_grids == 1 else jidx.to(device=grid.device, dtype=torch.int32).contiguous()
+    out = torch.empty((nq, w, w, w), dtype=torch.int64, device=grid.device)
+    with torch.cuda.device(grid.device):
+        check(lib.fvc_neighbor_indexes(grid.struct, _ptr(ijk), _ptr(bidx), nq, int(extent), int(bitshift), _ptr(out), _stream(grid.device)))
+    return out
+
+
+def ijk_to_index(grid: GridBatchData, ijk: torch.Tensor, jidx: "torch.Tensor | None", cumulative: bool = False) -> torch.Tensor:
+    _require_cuda(grid.device, "ijk_to_index")
+    ijk = _as_i32_coords(ijk.to(grid.device))
+    nq = int(ijk.shape[0])
+    bidx = None if jidx is None or grid.num_grids == 1 else jidx.to(device=grid.device, dtype=torch.int32).contiguous()
+    out = torch.empty(nq, dtype=torch.int64, device=grid.device)
+    with torch.cuda.device(grid.device):
+        check(lib.fvc_ijk_to_index(grid.struct, _ptr(ijk), _ptr(bidx), nq, int(cumulative), _ptr(out), _stream(grid.device)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# GatherScatterDefaultTopology (Bindings.cpp:542-561 over GatherScatterDefault.h:59-81)
+# ---------------------------------------------------------------------------------------------
+
+
+class _MapCore:
+    """Storage shared by a topology and its constant-time reversed view.
+
+    ``nbr`` is the output-stationary tap-major dense map of the *built* direction ([K^3, pitch] int32,
+    feature row or -1); ``nbr_rev`` (input-stationary, built lazily from the CSR pairs) serves dgrad of
+    the built direction and the forward pass of the reversed view.
+    """
+
+    def __init__(self, gather, scatter, offsets_host, offsets_dev, nbr, n_feature, n_output, kernel_volume):
+        self.gather, self.scatter = gather, scatter
+        self.offsets_host, self.offsets_dev = offsets_host, offsets_dev
+        self.nbr, self._nbr_rev = nbr, None
+        self.n_feature, self.n_output, self.kernel_volume = n_feature, n_output, kernel_volume
+        self.total_pairs = int(offsets_host[-1]) if offsets_host.numel() else 0
+
+    def nbr_rev(self) -> torch.Tensor:
+        if self._nbr_rev is None:
+            device = self.nbr.device
+            pitch = max(self.n_feature, 1)
+            rev = torch.empty((self.kernel_volume, pitch), dtype=torch.int32, device=device)
+            with torch.cuda.device(device):
+                check(
+                    lib.fvc_kmap_reverse_dense(
+                        _ptr(self.gather), _ptr(self.scatter), self.offsets_dev.data_ptr(), self.kernel_volume, self.total_pairs,
+                        self.n_feature, _ptr(rev), pitch, _stream(device),
+                    )
+                )
+            self._nbr_rev = rev
+        return self._nbr_rev
+
+
+class GatherScatterDefaultTopology:
+    """CSR-by-tap kernel map; same read-only properties as the reference binding."""
+
+    def __init__(self, core: _MapCore, kernel_size, stride, is_transposed: bool, reversed_view: bool):
+        self._core, self._reversed = core, reversed_view
+        self._kernel_size, self._stride, self._is_transposed = list(kernel_size), list(stride), bool(is_transposed)
+
+    gather_indices = property(lambda self: self._core.scatter if self._reversed else self._core.gather)
+    scatter_indices = property(lambda self: self._core.gather if self._reversed else self._core.scatter)
+    offsets = property(lambda self: self._core.offsets_host)
+    feature_total_voxels = property(lambda self: self._core.n_output if self._reversed else self._core.n_feature)
+    output_total_voxels = property(lambda self: self._core.n_feature if self._reversed else self._core.n_output)
+    kernel_volume = property(lambda self: self._core.kernel_volume)
+    total_pairs = property(lambda self: self._core.total_pairs)
+    kernel_size = property(lambda self: list(self._kernel_size))
+    stride = property(lambda self: list(self._stride))
+    is_transposed = property(lambda self: self._is_transposed)
+
+    # engine-private views
+    def _out_map(self) -> torch.Tensor:  # [K^3, pitch]: for each output row and tap, the feature row
+        return self._core.nbr_rev() if self._reversed else self._core.nbr
+
+    def _in_map(self) -> torch.Tensor:  # [K^3, pitch]: for each feature row and tap, the output row
+        return self._core.nbr if self._reversed else self._core.nbr_rev()
+
+    @property
+    def device(self) -> torch.device:
+        return self._core.nbr.device
+
+
+def _build_topology(feature_grid: GridBatchData, output_grid: GridBatchData, kernel_size, stride, transposed: bool) -> GatherScatterDefaultTopology:
+    ks, st = _vec3(kernel_size), _vec3(stride)
+    if feature_grid.device != output_grid.device:  # GatherScatterDefault.cu:58-62
+        raise RuntimeError(f"feature_grid and output_grid must be on the same device, got {feature_grid.device} and {output_grid.device}")
+    device = output_grid.device
+    _require_cuda(device, "gs_build_topology")
+    k3 = ks[0] * ks[1] * ks[2]
+    n_out, n_feat = output_grid.total_voxels, feature_grid.total_voxels
+    pitch = max(n_out, 1)
+    with torch.cuda.device(device):
+        stream = _stream(device)
+        nbr = torch.empty((k3, pitch), dtype=torch.int32, device=device)
+        tap_counts = torch.empty(k3, dtype=torch.int64, device=device)
+        check(lib.fvc_kmap_build(feature_grid.struct, output_grid.struct, i3(ks), i3(st), int(transposed), _ptr(nbr), pitch, tap_counts.data_ptr(), stream))
+        offsets_host = torch.zeros(k3 + 1, dtype=torch.int64)
+        offsets_host[1:] = torch.cumsum(tap_counts.cpu(), 0)  # the one D2H sync of the build (reference: GatherScatterDefault.cu:149)
+        total = int(offsets_host[-1])
+        gather = torch.empty(total, dtype=torch.int32, device=device)
+        scatter = torch.empty(total, dtype=torch.int32, device=device)
+        offsets_dev = torch.empty(k3 + 1, dtype=torch.int64, device=device)
+        scratch_bytes = int(lib.fvc_kmap_csr_scratch_bytes(n_out, k3))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device)
+        check(
+            lib.fvc_kmap_to_csr(
+                _ptr(nbr), pitch, n_out, k3, tap_counts.data_ptr(), offsets_dev.data_ptr(), _ptr(gather), _ptr(scatter), scratch.data_ptr(), scratch_bytes, stream
+            )
+        )
+    core = _MapCore(gather, scatter, offsets_host, offsets_dev, nbr, n_feat, n_out, k3)
+    return GatherScatterDefaultTopology(core, ks, st, transposed, reversed_view=False)
+
+
+def gs_build_topology(feature_grid, output_grid, kernel_size, stride) -> GatherScatterDefaultTopology:
+    """Forward kernel map (Bindings.cpp:570-583 -> gatherScatterDefaultSparseConvTopology)."""
+    return _build_topology(feature_grid, output_grid, kernel_size, stride, transposed=False)
+
+
+def gs_build_transpose_topology(feature_grid, output_grid, kernel_size, stride) -> GatherScatterDefaultTopology:
+    """Transposed kernel map (Bindings.cpp:612-625 -> gatherScatterDefaultSparseConvTransposeTopology)."""
+    return _build_topology(feature_grid, output_grid, kernel_size, stride, transposed=True)
+
+
+def gs_reverse_topology(topology: GatherScatterDefaultTopology) -> GatherScatterDefaultTopology:
+    """Constant-time reversed view aliasing the same tensors (GatherScatterDefault.cu:273-294)."""
+    return GatherScatterDefaultTopology(topology._core, topology._kernel_size, topology._stride, not topology._is_transposed, not topology._reversed)
+
+
+# ---------------------------------------------------------------------------------------------
+# Execution (Bindings.cpp:585-653 over GatherScatterDefault.cu:635-924)
+# ---------------------------------------------------------------------------------------------
+
+
+def _check_conv(features: torch.Tensor, weights: torch.Tensor, topo: GatherScatterDefaultTopology, name: str) -> None:
+    # GatherScatterDefault.cu:635-667
+    if features.dim() != 2:
+        raise RuntimeError(f"{name}: features must be 2D")
+    if features.size(0) != topo.feature_total_voxels:
+        raise RuntimeError(f"{name}: features.size(0)={features.size(0)} must match featureTotalVoxels={topo.feature_total_voxels}")
+    if not features.is_floating_point():
+        raise RuntimeError(f"{name}: features must be floating point")
+    if not features.is_contiguous():
+        raise RuntimeError(f"{name}: features must be contiguous")
+    if weights.dim() != 5:
+        raise RuntimeError(f"{name}: weights must be 5D [C_out, C_in, k0, k1, k2]")
+    if not weights.is_floating_point():
+        raise RuntimeError(f"{name}: weights must be floating point")
+    if features.size(1) != weights.size(1):
+        raise RuntimeError(f"{name}: features channels={features.size(1)} must match weights C_in={weights.size(1)}")
+    if list(weights.shape[2:]) != topo.kernel_size:
+        raise RuntimeError(f"{name}: weights spatial dims must match topology kernel_size")
+    if features.device != weights.device:
+        raise RuntimeError(f"{name}: features and weights must be on the same device")
+    _require_cuda(features.device, name)
+    if features.device != topo.device:
+        raise RuntimeError(f"{name}: features and topology must be on the same device")
+
+
+def _working_dtype(features: torch.Tensor, weights: torch.Tensor) -> torch.dtype:
+    working = torch.result_type(features, weights)  # promoteFloatTypes, GatherScatterDefault.cu:592-595
+    if working not in _DTYPE_CODE:
+        raise RuntimeError(f"no convolution kernel registered for dtype {working}")
+    return working
+
+
+def _pack_weights(weights: torch.Tensor, working: torch.dtype, layout: int) -> torch.Tensor:
+    cout, cin, k0, k1, k2 = weights.shape
+    out = torch.empty((k0 * k1 * k2, cin, cout) if layout == 0 else (k0 * k1 * k2, cout, cin), dtype=working, device=weights.device)
+    strides = (C.c_int64 * 5)(*weights.stride())
+    check(
+        lib.fvc_pack_weights(
+            _ptr(weights), C.byref(strides), _DTYPE_CODE[weights.dtype], cout, cin, k0, k1, k2, layout, 0, _DTYPE_CODE[working], _ptr(out), _stream(weights.device)
+        )
+    )
+    return out
+
+
+def _run_conv(x: torch.Tensor, w_packed: torch.Tensor, nbr: torch.Tensor, n_in: int, n_out: int, cin: int, cout: int, k3: int, bias: "torch.Tensor | None" = None) -> torch.Tensor:
+    device, dtype = x.device, x.dtype
+    y = torch.empty((n_out, cout), dtype=dtype, device=device)
+    if n_out == 0:
+        return y
+    code = _DTYPE_CODE[dtype]
+    scratch_bytes = int(lib.fvc_conv_scratch_bytes(n_out, cin, cout, k3, code))
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
+    check(
+        lib.fvc_conv_forward(
+            _ptr(x), _ptr(w_packed), _ptr(bias), y.data_ptr(), _ptr(nbr), int(nbr.shape[1]), n_in, n_out, cin, cout, k3, code, _path,
+            _ptr(scratch), scratch_bytes, _stream(device),
+        )
+    )
+    return y
+
+
+def _forward(features, weights, topo, name, want_transposed, bias=None):
+    _check_conv(features, weights, topo, name)
+    if topo.is_transposed != want_transposed:
+        raise RuntimeError(f"{name} requires topology with direction={'Transposed' if want_transposed else 'Forward'}")
+    working = _working_dtype(features, weights)
+    if features.dtype != working:
+        features = features.to(working)  # :850-852
+    cout, cin = int(weights.shape[0]), int(weights.shape[1])
+    with torch.cuda.device(features.device):
+        w = _pack_weights(weights, working, layout=0)
+        if bias is not None:
+            bias = bias.to(device=features.device, dtype=working).contiguous()
+        return _run_conv(features, w, topo._out_map(), topo.feature_total_voxels, topo.output_total_voxels, cin, cout, topo.kernel_volume, bias)
+
+
+def _backward(grad_output, features, weights, topo, name, want_transposed):
+    _check_conv(features, weights, topo, name)
+    if topo.is_transposed != want_transposed:
+        raise RuntimeError(f"{name} requires {'direction=Transposed' if want_transposed else 'topology with direction=Forward'}")
+    if grad_output.dim() != 2 or grad_output.size(0) != topo.output_total_voxels:
+        raise RuntimeError("grad_output shape mismatch")  # :869-870
+    if not grad_output.is_contiguous():
+        raise RuntimeError("grad_output must be contiguous")
+    if not grad_output.is_floating_point():
+        raise RuntimeError("grad_output must be floating point")
+    working = _working_dtype(features, weights)
+    features = features.to(working) if features.dtype != working else features
+    grad_output = grad_output.to(working) if grad_output.dtype != working else grad_output
+    cout, cin = int(weights.shape[0]), int(weights.shape[1])
+    k3, n_feat, n_out = topo.kernel_volume, topo.feature_total_voxels, topo.output_total_voxels
+    if grad_output.size(1) != cout:
+        raise RuntimeError("grad_output shape mismatch")
+    device = features.device
+    code = _DTYPE_CODE[working]
+    with torch.cuda.device(device):
+        # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (GatherScatterDefault.cu:803-804), output-stationary over features
+        wt = _pack_weights(weights, working, layout=1)
+        if n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
+            grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
+        else:
+            grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3)
+        # wgrad: dW[k] = X[g]^T . dY[s]  (:806-813)
+        grad_weights = torch.empty(tuple(weights.shape), dtype=working, device=device)
+        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_out, topo.total_pairs, cin, cout, k3, code))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
+        offsets_host = topo.offsets
+        out_map = topo._out_map()
+        check(
+            lib.fvc_conv_wgrad(
+                _ptr(features), _ptr(grad_output), _ptr(topo.gather_indices), _ptr(topo.scatter_indices),
+                C.cast(offsets_host.data_ptr(), C.POINTER(C.c_int64)), topo._core.offsets_dev.data_ptr(), _ptr(out_map), int(out_map.shape[1]),
+                n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
+            )
+        )
+    return grad_features, grad_weights
+
+
+def gs_conv(features, weights, topology, bias=None):
+    """Forward sparse convolution (Bindings.cpp:585-594)."""
+    return _forward(features, weights, topology, "gatherScatterDefaultSparseConv", False, bias)
+
+
+def gs_conv_backward(grad_output, features, weights, topology):
+    """(grad_features, grad_weights) of the forward convolution (Bindings.cpp:595-609)."""
+    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvBackward", False)
+
+
+def gs_conv_transpose(features, weights, topology, bias=None):
+    """Forward transposed sparse convolution (Bindings.cpp:627-637)."""
+    return _forward(features, weights, topology, "gatherScatterDefaultSparseConvTranspose", True, bias)
+
+
+def gs_conv_transpose_backward(grad_output, features, weights, topology):
+    """(grad_features, grad_weights) of the transposed convolution (Bindings.cpp:638-653)."""
+    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvTransposeBackward", True)
+
+
+def pred_gather_igemm_conv(features, weights, feature_grid, output_grid, kernel_size: int, stride: int):
+    """Tensor-core forward (Bindings.cpp:657-674 -> predGatherIGemmSparseConv, PredGatherIGemm.cu:1121-1172).
+
+    The reference's SM80 TF32 leaf-blocked kernel is replaced by the same tcgen05 implicit-GEMM engine that
+    serves ``gs_conv``; this entry point keeps the reference's admission checks and builds the map on the fly.
+    """
+    if features.dim() != 2 or weights.dim() != 5:
+        raise RuntimeError("predGatherIGemmSparseConv: features must be 2D and weights 5D")
+    if features.size(1) % 32 or weights.size(0) % 32:
+        raise RuntimeError("predGatherIGemmSparseConv requires channel counts divisible by 32")
+    if feature_grid.grid_count != 1 or output_grid.grid_count != 1:
+        raise RuntimeError("predGatherIGemmSparseConv supports only batch size 1")
+    topology = gs_build_topology(feature_grid, output_grid, [kernel_size] * 3, [stride] * 3)
+    return gs_conv(features, weights, topology)

@@ -1,0 +1,146 @@
+"""``GridBatch``: the subset of the reference's grid API the convolution path uses.
+
+Mirrors the names and meaning of reference fvdb/grid_batch.py (``from_ijk:220``, ``conv_grid:582``,
+``conv_transpose_grid:606``, ``jagged_like:1026``, ``neighbor_indexes:1181``, ``ijk:1944``, ``grid_count:1926``,
+``total_voxels:2084``, ``is_same:1013``, ``voxel_sizes`` / ``origins``).  Everything else in the reference's
+~100-method grid API (sampling, rays, meshing, IO ...) is outside the ConvolutionPlan path.
+Grids live on a CUDA device; there is no CPU grid in this build.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _fvdb_cpp
+from .jagged_tensor import JaggedTensor
+from .types import NumericMaxRank1, NumericMaxRank2, ValueConstraint, to_Vec3fBatch, to_Vec3i
+
+
+class GridBatch:
+    def __init__(self, data: _fvdb_cpp.GridBatchData):
+        if not isinstance(data, _fvdb_cpp.GridBatchData):
+            raise TypeError("GridBatch wraps a GridBatchData; use GridBatch.from_ijk(...)")
+        self.data = data
+
+    # ---- construction ---------------------------------------------------------------------
+    @classmethod
+    def from_ijk(cls, ijk: "JaggedTensor | torch.Tensor", voxel_sizes: NumericMaxRank2 = 1, origins: NumericMaxRank2 = 0) -> "GridBatch":
+        """Grid batch from explicit voxel coordinates (duplicates and negative coordinates allowed)."""
+        if isinstance(ijk, torch.Tensor):
+            ijk = JaggedTensor(ijk)
+        num_grids = ijk.num_tensors
+        sizes = to_Vec3fBatch(voxel_sizes, num_grids, "voxel_sizes", positive=True)
+        orig = to_Vec3fBatch(origins, num_grids, "origins")
+        coords = ijk.jdata.reshape(-1, 3) if ijk.jdata.numel() == 0 else ijk.jdata
+        data = _fvdb_cpp.build_grid_from_ijk(coords, ijk.jidx if num_grids > 1 else None, num_grids, sizes, orig)
+        return cls(data)
+
+    @classmethod
+    def from_zero_voxels(cls, device="cuda", voxel_sizes: NumericMaxRank2 = 1, origins: NumericMaxRank2 = 0) -> "GridBatch":
+        sizes = torch.as_tensor(voxel_sizes, dtype=torch.float64).reshape(-1, 3) if not isinstance(voxel_sizes, (int, float)) else None
+        num_grids = 1 if sizes is None else int(sizes.shape[0])
+        empty = [torch.zeros((0, 3), dtype=torch.int32, device=device) for _ in range(num_grids)]
+        return cls.from_ijk(JaggedTensor(empty), voxel_sizes, origins)
+
+    # ---- metadata -------------------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return self.data.device
+
+    @property
+    def grid_count(self) -> int:
+        return self.data.num_grids
+
+    def __len__(self) -> int:
+        return self.data.num_grids
+
+    @property
+    def total_voxels(self) -> int:
+        return self.data.total_voxels
+
+    @property
+    def total_leaf_nodes(self) -> int:
+        return self.data.num_leaves
+
+    @property
+    def num_voxels(self) -> torch.Tensor:
+        offsets = self.data.voxel_offsets
+        return offsets[1:] - offsets[:-1]
+
+    def num_voxels_at(self, bi: int) -> int:
+        return int(self.num_voxels[bi].item())
+
+    @property
+    def joffsets(self) -> torch.Tensor:
+        return self.data.voxel_offsets
+
+    @property
+    def jidx(self) -> torch.Tensor:
+        return self.data.jidx
+
+    @property
+    def voxel_sizes(self) -> torch.Tensor:
+        return self.data.voxel_sizes.to(device=self.device, dtype=torch.float32)
+
+    @property
+    def origins(self) -> torch.Tensor:
+        return self.data.origins.to(device=self.device, dtype=torch.float32)
+
+    @property
+    def ijk(self) -> JaggedTensor:
+        """Voxel coordinates in row order, one tensor per grid."""
+        return JaggedTensor(_data=self.data.ijk, _offsets=self.data.voxel_offsets, _jidx=self.data.jidx)
+
+    def is_same(self, other: "GridBatch") -> bool:
+        return self.data.is_same(other.data)
+
+    def jagged_like(self, data: torch.Tensor) -> JaggedTensor:
+        """Wrap ``data [total_voxels, ...]`` with this batch's per-grid structure."""
+        if data.shape[0] != self.total_voxels:
+            raise ValueError(f"data has {data.shape[0]} rows but the grid batch has {self.total_voxels} voxels")
+        jidx = self.data.jidx
+        return JaggedTensor(_data=data, _offsets=self.data.voxel_offsets.to(data.device), _jidx=jidx.to(data.device))
+
+    # ---- generated convolution topologies --------------------------------------------------
+    def conv_grid(self, kernel_size: NumericMaxRank1, stride: NumericMaxRank1 = 1) -> "GridBatch":
+        """Complete structural support of a convolution on this batch (voxel size * stride, same origin).
+        ``kernel_size = stride = 1`` returns ``self`` (reference functional/_topology.py:452-453)."""
+        ks = to_Vec3i(kernel_size, value_constraint=ValueConstraint.POSITIVE).tolist()
+        st = to_Vec3i(stride, value_constraint=ValueConstraint.POSITIVE).tolist()
+        if ks == [1, 1, 1] and st == [1, 1, 1]:
+            return self
+        return GridBatch(_fvdb_cpp.conv_grid(self.data, ks, st))
+
+    def conv_transpose_grid(self, kernel_size: NumericMaxRank1, stride: NumericMaxRank1 = 1) -> "GridBatch":
+        """Complete structural support of a transposed convolution (voxel size / stride, same origin)."""
+        ks = to_Vec3i(kernel_size, value_constraint=ValueConstraint.POSITIVE).tolist()
+        st = to_Vec3i(stride, value_constraint=ValueConstraint.POSITIVE).tolist()
+        if ks == [1, 1, 1] and st == [1, 1, 1]:
+            return self
+        return GridBatch(_fvdb_cpp.conv_transpose_grid(self.data, ks, st))
+
+    # ---- lookups ----------------------------------------------------------------------------
+    def _query(self, ijk: "JaggedTensor | torch.Tensor") -> JaggedTensor:
+        if isinstance(ijk, torch.Tensor):
+            ijk = JaggedTensor(ijk)
+        if ijk.num_tensors != self.grid_count:
+            raise ValueError(f"query has {ijk.num_tensors} tensors but the grid batch has {self.grid_count} grids")
+        return ijk
+
+    def neighbor_indexes(self, ijk: "JaggedTensor | torch.Tensor", extent: int, bitshift: int = 0) -> JaggedTensor:
+        """Per-grid-local index (or -1) of every voxel in ``[-extent, extent]^3`` around each query."""
+        q = self._query(ijk)
+        out = _fvdb_cpp.neighbor_indexes(self.data, q.jdata, q.jidx if self.grid_count > 1 else None, extent, bitshift)
+        return q.jagged_like(out)
+
+    def ijk_to_index(self, ijk: "JaggedTensor | torch.Tensor", cumulative: bool = False) -> JaggedTensor:
+        q = self._query(ijk)
+        out = _fvdb_cpp.ijk_to_index(self.data, q.jdata, q.jidx if self.grid_count > 1 else None, cumulative)
+        return q.jagged_like(out)
+
+    def coords_in_grid(self, ijk: "JaggedTensor | torch.Tensor") -> JaggedTensor:
+        idx = self.ijk_to_index(ijk)
+        return idx.jagged_like(idx.jdata >= 0)
+
+    def __repr__(self) -> str:
+        return f"GridBatch(grid_count={self.grid_count}, total_voxels={self.total_voxels}, device={self.device})"

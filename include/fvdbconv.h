@@ -1,0 +1,218 @@
+/*
+ * fvdbconv.h -- C ABI of the B200-native sparse-convolution engine (libfvdbconv.so).
+ *
+ * This library is the drop-in for the convolution section of fVDB's pybind11 module
+ * `fvdb._fvdb_cpp` (reference: src/python/Bindings.cpp:491-674 and src/python/GridBatchOps.cpp:764-792)
+ * and for the C++ ops those bindings call (src/fvdb/detail/ops/convolution/GatherScatterDefault.{h,cu},
+ * PredGatherIGemm.{h,cu}, ops/BuildGridForConv*.cu, ops/BuildGridFromIjk.cu, ops/NeighborIndexes.cu).
+ * Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw device pointers (tensor.data_ptr()), sizes, an explicit stream;
+ *   - the library never allocates or frees user-visible memory: outputs and scratch are allocated by
+ *     the caller (PyTorch's caching allocator owns everything);
+ *   - every call is asynchronous on `stream` unless the comment says it synchronises (only the calls
+ *     that must return a count to size the caller's next allocation do);
+ *   - return value 0 = success, non-zero = failure; fvc_last_error() gives the thread-local message.
+ *     The Python shim maps FVC_ERR_VALUE -> ValueError, FVC_ERR_INDEX -> IndexError, others ->
+ *     RuntimeError, as TORCH_CHECK_VALUE / TORCH_CHECK_INDEX / TORCH_CHECK do in the reference;
+ *   - there is no CPU fallback: every compute entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef FVDBCONV_H
+#define FVDBCONV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FVC_API __attribute__((visibility("default")))
+#else
+#define FVC_API
+#endif
+
+/* status codes */
+#define FVC_OK 0
+#define FVC_ERR_VALUE 1       /* invalid argument value   (reference: TORCH_CHECK_VALUE -> ValueError)   */
+#define FVC_ERR_RUNTIME 2     /* precondition violated    (reference: TORCH_CHECK       -> RuntimeError) */
+#define FVC_ERR_INDEX 3       /* index out of range       (reference: TORCH_CHECK_INDEX -> IndexError)   */
+#define FVC_ERR_CUDA 4        /* CUDA runtime failure                                                    */
+#define FVC_ERR_UNSUPPORTED 5 /* no kernel for this dtype / shape (reference: dispatch_lookup_error)     */
+
+/* dtype codes (torch.float16 / bfloat16 / float32 / float64) */
+#define FVC_F16 0
+#define FVC_BF16 1
+#define FVC_F32 2
+#define FVC_F64 3
+
+typedef void *fvc_stream_t; /* cudaStream_t */
+
+/* -------------------------------------------------------------------------------------------------
+ * Index grid (replaces the NanoVDB OnIndexGrid batch held by fvdb::GridBatchData,
+ * reference: src/fvdb/GridBatchData.h:29-55,120-226).
+ *
+ * Tree shape follows NanoVDB: root (sorted table of 4096^3 tiles per grid) -> upper node 32^3 ->
+ * lower node 16^3 -> leaf 8^3.  One leaf is one 128-byte record = one L2 line:
+ *   mask[w] bit (y&7)*8+(z&7) for w = x&7;  prefix[w] = number of active voxels in words < w;
+ *   value(x,y,z) = base + prefix[w] + popcount(mask[w] below the bit)  (0-based, batch-cumulative row).
+ * Voxel rows are ordered by (grid, root tile, upper offset, lower offset, leaf offset), each x-major.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct FvcLeaf {
+    uint64_t mask[8];
+    uint16_t prefix[8];
+    int32_t base;      /* batch-cumulative row of the leaf's first active voxel */
+    int32_t batch;     /* grid index inside the batch */
+    int32_t origin[3]; /* ijk of the leaf's (0,0,0) corner, multiples of 8 */
+    int32_t count;     /* active voxels in this leaf */
+    int32_t reserved[6];
+} FvcLeaf; /* sizeof == 128 */
+
+typedef struct FvcGridBatch {
+    int32_t num_grids;
+    int32_t num_leaves;
+    int32_t num_lower;
+    int32_t num_upper; /* == number of root tiles */
+    int64_t total_voxels;
+    const FvcLeaf *leaves;        /* [num_leaves], 128-byte aligned                                  */
+    const int32_t *lower;         /* [num_lower][4096]   leaf index or -1                            */
+    const int32_t *upper;         /* [num_upper][32768]  lower-node index or -1                      */
+    const int32_t *root_keys;     /* [num_upper][4]      (grid, x>>12, y>>12, z>>12), sorted         */
+    const int32_t *root_offsets;  /* [num_grids+1]       range of root tiles owned by each grid      */
+    const int64_t *voxel_offsets; /* [num_grids+1]       cumulative voxel count (JaggedTensor joffsets) */
+    const int32_t *leaf_offsets;  /* [num_grids+1]       cumulative leaf count                       */
+} FvcGridBatch;
+
+/* -------- library / device ------------------------------------------------------------------- */
+FVC_API int fvc_abi_version(void);
+FVC_API const char *fvc_last_error(void);
+/* Fills sm_count / cc_major / cc_minor of the current device; fails (FVC_ERR_CUDA) without a GPU. */
+FVC_API int fvc_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+FVC_API int64_t fvc_launch_count(void);
+
+/* -------- geometry (host-only; replaces ConvolutionGeometry.h:30-207) ----------------------------- */
+/* Validates kernel_size / stride (> 0, volume fits int64) and returns padding_before / padding_after /
+ * kernel_volume.  FVC_ERR_VALUE mirrors TORCH_CHECK_VALUE at ConvolutionGeometry.h:150-172,186-198. */
+FVC_API int fvc_geometry(const int32_t kernel_size[3], const int32_t stride[3], int32_t padding_before[3],
+                 int32_t padding_after[3], int64_t *kernel_volume);
+/* tapCoord (ConvolutionGeometry.h:85-90), fineFromCoarse (:99-104), coarseFromFine (:107-124; returns
+ * *divisible = 0 and leaves coarse untouched when an axis does not divide). */
+FVC_API int fvc_geometry_tap_coord(const int32_t kernel_size[3], int64_t tap_index, int32_t tap[3]);
+FVC_API int fvc_geometry_fine_from_coarse(const int32_t kernel_size[3], const int32_t stride[3], const int32_t coarse[3],
+                                  const int32_t tap[3], int32_t fine[3]);
+FVC_API int fvc_geometry_coarse_from_fine(const int32_t kernel_size[3], const int32_t stride[3], const int32_t fine[3],
+                                  const int32_t tap[3], int32_t coarse[3], int32_t *divisible);
+
+/* -------- index-grid construction (replaces ops/BuildGridFromIjk.cu:52-111, NanoVDB voxelsToGrid) -- */
+/* Scratch bytes needed by fvc_grid_build_* for n input coordinates. */
+FVC_API size_t fvc_grid_build_scratch_bytes(int64_t n);
+/* Stage 1: sort the (grid, ijk) keys into index-grid row order, mark duplicates, count nodes.
+ * ijk: int32 [n][3]; bidx: int32 [n] grid index of each row (NULL = all grid 0); coordinates may be
+ * negative and duplicated.  counts_host[0..3] = {unique voxels, leaves, lower nodes, upper nodes}.
+ * SYNCHRONISES the stream (the caller sizes the node arrays from the counts). */
+FVC_API int fvc_grid_build_count(const int32_t *ijk, const int32_t *bidx, int64_t n, int32_t num_grids, void *scratch,
+                         size_t scratch_bytes, int64_t counts_host[4], fvc_stream_t stream);
+/* Stage 2: fill caller-allocated node arrays (sized from counts_host) and the row-ordered ijk table.
+ * `scratch` must be the buffer stage 1 wrote; the call initialises every output itself.  out_ijk: int32 [unique][3]; out_bidx: int32 [unique] (JaggedTensor jidx). */
+FVC_API int fvc_grid_build_fill(const int32_t *ijk, const int32_t *bidx, int64_t n, int32_t num_grids, void *scratch,
+                        size_t scratch_bytes, const int64_t counts_host[4], FvcLeaf *leaves, int32_t *lower,
+                        int32_t *upper, int32_t *root_keys, int32_t *root_offsets, int64_t *voxel_offsets,
+                        int32_t *leaf_offsets, int32_t *out_ijk, int32_t *out_bidx, fvc_stream_t stream);
+
+/* -------- generated target topologies (replaces conv_grid / conv_transpose_grid,
+ *          src/python/GridBatchOps.cpp:764-792, ops/BuildGridForConv.cu:392-544,
+ *          ops/BuildGridForConvTranspose.cu:201-359) ------------------------------------------- */
+/* Number of candidate target coordinates the source grid emits (forward: one per divisible tap per
+ * voxel; transposed: voxels * kernel volume).  SYNCHRONISES (forward only). */
+FVC_API int fvc_conv_grid_count(const int32_t *src_ijk, int64_t n, const int32_t kernel_size[3], const int32_t stride[3],
+                        int32_t transposed, void *scratch8, int64_t *count_host, fvc_stream_t stream);
+/* Emits the candidates (unsorted, with duplicates) into cand_ijk [count][3] / cand_bidx [count]; feed
+ * them to fvc_grid_build_*.  counter8: 8 bytes of zero-initialised-by-the-call device scratch. */
+FVC_API int fvc_conv_grid_emit(const int32_t *src_ijk, const int32_t *src_bidx, int64_t n, const int32_t kernel_size[3],
+                       const int32_t stride[3], int32_t transposed, int64_t count, int32_t *cand_ijk,
+                       int32_t *cand_bidx, void *counter8, fvc_stream_t stream);
+
+/* -------- kernel map (replaces gs_build_topology / gs_build_transpose_topology,
+ *          Bindings.cpp:570-583,612-625 -> GatherScatterDefault.cu:92-271) --------------------- */
+/* Output-stationary, tap-major dense map: nbr[k * pitch + o] = feature row reached from output row o
+ * through tap k, or -1.  Forward probes fineFromCoarse on the feature grid, transposed probes
+ * coarseFromFine with the divisibility test (GatherScatterDefault.cu:129-141); probes never leave the
+ * output voxel's own grid (:126).  tap_counts: int64 [K^3] device, number of pairs per tap.
+ * FVC_ERR_RUNTIME when either grid exceeds INT32_MAX voxels or batch sizes differ (:58-80). */
+FVC_API int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_grid, const int32_t kernel_size[3],
+                   const int32_t stride[3], int32_t transposed, int32_t *nbr, int64_t pitch, int64_t *tap_counts,
+                   fvc_stream_t stream);
+/* CSR-by-tap view of a dense map (GatherScatterDefaultTopology, GatherScatterDefault.h:59-81): per tap
+ * segment, pairs ordered by output row.  offsets_dev: int64 [K^3+1] = exclusive scan of tap_counts
+ * (written by the call); gather / scatter: int32 [total pairs].  scratch: fvc_kmap_csr_scratch_bytes. */
+FVC_API size_t fvc_kmap_csr_scratch_bytes(int64_t n_out, int64_t kernel_volume);
+FVC_API int fvc_kmap_to_csr(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume,
+                    const int64_t *tap_counts, int64_t *offsets_dev, int32_t *gather, int32_t *scatter, void *scratch,
+                    size_t scratch_bytes, fvc_stream_t stream);
+/* Dense map of the reversed rulebook from a CSR view: nbr_rev[k * pitch_rev + gather[p]] = scatter[p]
+ * (the input-stationary map dgrad consumes; GatherScatterDefault.cu:794-804).  Fills -1 first. */
+FVC_API int fvc_kmap_reverse_dense(const int32_t *gather, const int32_t *scatter, const int64_t *offsets_dev,
+                           int64_t kernel_volume, int64_t total_pairs, int64_t n_feature, int32_t *nbr_rev,
+                           int64_t pitch_rev, fvc_stream_t stream);
+/* Per-row degree (number of taps that hit) of a dense map: degree int32 [n_out]. */
+FVC_API int fvc_kmap_degree(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, int32_t *degree,
+                    fvc_stream_t stream);
+
+/* -------- lookups (replaces ops/NeighborIndexes.cu:22-121, ops/IjkToIndex.cu:30-40) ------------- */
+/* out: int64 [nq][w][w][w], w = 2*extent+1, x-major offsets in [-extent, extent]; per-grid-local index
+ * or -1; query ijk is shifted left by `shift` first (NeighborIndexes.cu:35-44). */
+FVC_API int fvc_neighbor_indexes(const FvcGridBatch *grid, const int32_t *query_ijk, const int32_t *query_bidx, int64_t nq,
+                         int32_t extent, int32_t shift, int64_t *out, fvc_stream_t stream);
+/* out: int64 [nq]; per-grid-local (cumulative = 0) or batch-cumulative (cumulative = 1) row, or -1. */
+FVC_API int fvc_ijk_to_index(const FvcGridBatch *grid, const int32_t *query_ijk, const int32_t *query_bidx, int64_t nq,
+                     int32_t cumulative, int64_t *out, fvc_stream_t stream);
+
+/* -------- weights ----------------------------------------------------------------------------------
+ * Replaces `weights.permute({2,3,4,1,0}).reshape({K,Cin,Cout}).contiguous()` (+ cast)
+ * (GatherScatterDefault.cu:691-694,762-765).  Reads public-layout weights [Cout,Cin,k0,k1,k2] through
+ * arbitrary element strides (fvdb.nn stores them as a permuted view, fvdb/nn/modules.py:282-289).
+ *   layout 0: out[k][ci][co]   (forward:  Y  = X  . W[k])
+ *   layout 1: out[k][co][ci]   (dgrad:    dX = dY . W[k]^T)
+ * flip_taps != 0 writes tap k to slot K-1-k (dgrad of a same-grid stride-1 odd-K plan reuses the
+ * forward map with flipped taps). */
+FVC_API int fvc_pack_weights(const void *weights, const int64_t strides[5], int32_t dtype_in, int32_t cout, int32_t cin,
+                     int32_t k0, int32_t k1, int32_t k2, int32_t layout, int32_t flip_taps, int32_t dtype_out, void *out,
+                     fvc_stream_t stream);
+
+/* -------- execution (replaces gs_conv / gs_conv_transpose / gs_conv_backward /
+ *          gs_conv_transpose_backward / pred_gather_igemm_conv, Bindings.cpp:585-674 ->
+ *          GatherScatterDefault.cu:673-924, PredGatherIGemm.cu:1121-1172) ----------------------- */
+/* Output-stationary sparse convolution: y[o,:] = sum_k x[nbr[k*pitch+o],:] . w[k]   (w: [K][Cin][Cout]).
+ * One entry point serves forward (either direction) and dgrad (x = grad_output, nbr = the reversed
+ * map, w packed with layout 1): the maps are already oriented (GatherScatterDefault.cu:734-740).
+ * x, y, w share `dtype`; accumulation is fp32 (fp64 for FVC_F64).  y is fully overwritten (rows with
+ * no neighbour become 0; GatherScatterDefault.cu:696).  bias (may be NULL): [Cout] in `dtype`, added in
+ * the epilogue (fvdb/nn/modules.py:370-371).  path: 0 = automatic (tensor-core kernel when dtype is
+ * f16/bf16 and the channel counts allow it, else the CUDA-core kernel), 1 = force CUDA-core path,
+ * 2 = force tensor-core path (FVC_ERR_UNSUPPORTED if not admissible). */
+FVC_API size_t fvc_conv_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype);
+FVC_API int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
+                     int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                     int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
+/* Weight gradient: grad_w[co][ci][k0][k1][k2] = sum over pairs p of tap k of x[gather[p]][ci] * dy[scatter[p]][co]
+ * (GatherScatterDefault.cu:806-813), written contiguous in the public layout in `dtype`;
+ * fixed-order (deterministic) fp32/fp64 reduction.  offsets_host / offsets_dev: the same int64 [K^3+1]
+ * CSR offsets on the host and on the device.  nbr/pitch: the output-stationary dense map of the same
+ * rulebook (used by the tensor-core path; may be NULL, then the CSR path runs). */
+FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout,
+                                    int64_t kernel_volume, int32_t dtype);
+FVC_API int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const int32_t *scatter,
+                   const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
+                   int64_t n_in, int64_t n_out,
+                   int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, void *grad_w,
+                   void *scratch, size_t scratch_bytes, fvc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVDBCONV_H */
