@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- sparse-conv voxels/sec forward+backward over a GridBatch (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c4|c5]
+
+One "step" = one pass of the hot path over one batch: forward + dgrad + wgrad of a 3^3 64->64 bf16
+SparseConv3d-shaped plan (BASELINE.json configs[1]: 8 indoor grids x ~200 k voxels, same-topology target),
+kernel map prebuilt ("topology amortized", as the reference's own benches do).  For N > 1 (launched under
+torch.distributed.run) every rank owns whole grids (its own batch of 8: weak scaling) and the step ends
+with the NCCL all-reduce of grad_weights, the path's only exchange.
+
+Prints ONE JSON line on rank 0; see the task contract for the keys.  `value` is timed with inputs
+resident in HBM; `e2e` goes through the same C-ABI-backed calls with HOST (pinned) buffers, H2D and D2H
+copies inside the timed region.  `--impl reference` times the CPU restatement of the reference's own
+CPU path (oracle/, torch::mm semantics, all host threads) on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+for p in (str(REPO), str(REPO / "fvdb-core_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (generator, grids, target voxels per grid, kernel, cin, cout, dtype)
+    "c1": dict(gen="sphere_shell", grids=1, voxels=100_000, kernel=3, cin=32, cout=32, dtype="f32", desc="C1 single grid ~100k voxels, 3^3 32->32 fp32"),
+    "c2": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=64, cout=64, dtype="bf16", desc="C2 ScanNet-shaped 8 grids x ~200k voxels, 3^3 64->64 bf16 fwd+bwd"),
+    "c4": dict(gen="lidar_sweep", grids=32, voxels=1_000_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C4 KITTI-shaped 32 grids x ~1M voxels, 3^3 128->128 bf16"),
+    "c5": dict(gen="random_occupancy", grids=8, voxels=4_979_000, kernel=5, cin=16, cout=16, dtype="bf16", desc="C5 8 grids x ~5M voxels, 5^3 16->16"),
+}
+DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16, "f64": torch.float64}
+
+
+def load_peaks() -> dict:
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        d = json.loads(path.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def make_coords(cfg: dict, rank: int, device) -> list[torch.Tensor]:
+    from fvdb.utils import synthetic
+
+    gen = getattr(synthetic, cfg["gen"])
+    out = []
+    for g in range(cfg["grids"]):
+        seed = rank * 1000 + g
+        if cfg["gen"] == "random_occupancy":
+            out.append(gen(seed=42 + seed, device=device))
+        else:
+            out.append(gen(target=cfg["voxels"], seed=seed, device="cpu").to(device))
+    return out
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([f.strip() for f in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(P, n_in, n_out, cin, cout, k3, s):
+    """gathered bytes per pass."""
+    return {
+        "fwd": P * cin * s + n_out * cout * s + 4 * P + k3 * cin * cout * s,
+        "dgrad": P * cout * s + n_in * cin * s + 4 * P + k3 * cin * cout * s,
+        "wgrad": P * (cin + cout) * s + 8 * P + 4 * k3 * cin * cout,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference's CPU path on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+
+
+def cpu_reference_step_time(cfg: dict, sample_grids: int, repeats: int, warmup: int):
+    """Seconds per fwd+bwd of the oracle (per-tap index_select -> mm -> index_add_, fp32, all host threads)
+    on `sample_grids` grids of the workload.  Returns (seconds per step, voxels per step, pairs, threads)."""
+    import oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    coords = make_coords({**cfg, "grids": sample_grids}, 0, "cpu")
+    ijk = torch.cat(coords).numpy().astype(np.int64)
+    bidx = np.concatenate([np.full(len(c), i, dtype=np.int64) for i, c in enumerate(coords)])
+    order = oracle.index_grid_row_order(bidx, ijk)
+    ijk, bidx = ijk[order], bidx[order]
+    k = cfg["kernel"]
+    topo = oracle.build_topology(ijk, bidx, ijk, bidx, k, 1)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn((len(ijk), cfg["cin"]), generator=gen)
+    w = (torch.rand((cfg["cout"], cfg["cin"], k, k, k), generator=gen) * 2 - 1) / (cfg["cin"] * k**3) ** 0.5
+    dy = torch.randn((len(ijk), cfg["cout"]), generator=gen)
+    times, begin = [], time.perf_counter()
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        oracle.gs_conv(x, w, topo)
+        oracle.gs_conv_backward(dy, x, w, topo)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+        if times and time.perf_counter() - begin > 150.0:  # keep the whole run within a few minutes
+            break
+    return float(np.median(times)), len(ijk), topo.total_pairs, torch.get_num_threads()
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_grids = 1
+    sec, voxels, pairs, threads = cpu_reference_step_time(cfg, sample_grids, max(1, args.steps), max(0, min(args.warmup, 2)))
+    value = voxels / sec
+    line = {
+        "impl": "reference", "metric": "sparse-conv voxels/sec fwd+bwd", "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": cfg["desc"], "sample": f"{sample_grids} of {cfg['grids']} grids per step ({voxels} voxels, {pairs} pairs)"},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_grids} grid ({voxels} voxels) fwd+bwd fp32 per step, oracle port of GatherScatterDefault CPU path"},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+
+
+def run_ours(args, cfg):
+    import torch.distributed as dist
+
+    import fvdb
+    from fvdb import _fvdb_cpp as cpp
+    from fvdb._lib import launch_count
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dtype = DTYPES[cfg["dtype"]]
+    k, cin, cout = cfg["kernel"], cfg["cin"], cfg["cout"]
+    coords = make_coords(cfg, rank, dev)
+    grid = fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(coords))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid)
+    topo = plan._backend.topology
+    topo._in_map()  # reversed dense map for dgrad is part of the (amortised) plan
+    torch.cuda.synchronize()
+    plan_ms = (time.perf_counter() - t0) * 1e3
+    n, P, k3 = grid.total_voxels, topo.total_pairs, topo.kernel_volume
+
+    gen = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.randn((n, cin), generator=gen).to(dtype).pin_memory()
+    dy_host = torch.randn((n, cout), generator=gen).to(dtype).pin_memory()
+    w = ((torch.rand((cout, cin, k, k, k), generator=gen) * 2 - 1) / (cin * k**3) ** 0.5).to(dtype).to(dev)
+    x, dy = x_host.to(dev), dy_host.to(dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    phase_ms = {"fwd": [], "dgrad+wgrad": []}
+
+    def step(record: bool):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        y = cpp.gs_conv(x, w, topo)
+        e1.record()
+        gx, gw = cpp.gs_conv_backward(dy, x, w, topo)
+        if world > 1:
+            dist.all_reduce(gw)
+        e2.record()
+        if record:
+            phase_ms["fwd"].append((e0, e1))
+            phase_ms["dgrad+wgrad"].append((e1, e2))
+        return y, gx, gw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    launches0 = launch_count()
+    with ClockSampler(local_rank) as clocks:
+        start, stop = ev(), ev()
+        start.record()
+        for _ in range(args.steps):
+            step(True)
+        stop.record()
+        barrier()
+    launches = launch_count() - launches0
+    ms = start.elapsed_time(stop) / args.steps
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in phase_ms["fwd"]]))
+    bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in phase_ms["dgrad+wgrad"]]))
+
+    # per-kernel durations of the three hot kernels, each timed alone on the launching stream
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    code = cpp._DTYPE_CODE[dtype]
+    w_fwd = cpp._pack_weights(w, dtype, 0)
+    w_bwd = cpp._pack_weights(w, dtype, 1)
+    out_map, in_map = topo._out_map(), topo._in_map()
+    kern_ms = {
+        "fwd": timed(lambda: cpp._run_conv(x, w_fwd, out_map, n, n, cin, cout, k3), max(3, args.steps)),
+        "dgrad": timed(lambda: cpp._run_conv(dy, w_bwd, in_map, n, n, cout, cin, k3), max(3, args.steps)),
+    }
+    kern_ms["wgrad"] = max(bwd_ms - kern_ms["dgrad"], 1e-6)
+    peaks = load_peaks()
+    s = x.element_size()
+    abytes = algorithmic_bytes(P, n, n, cin, cout, k3, s)
+    flops = 2.0 * P * cin * cout
+    dominant = max(kern_ms, key=kern_ms.get)
+    per_kernel = {}
+    for name in kern_ms:
+        t = kern_ms[name] * 1e-3
+        hbm_t, tensor_t = abytes[name] / (peaks["hbm_gbs"] * 1e9), flops / (peaks["tflops"] * 1e12)
+        bound = "hbm" if hbm_t >= tensor_t else "tensor"
+        achieved = abytes[name] / t / 1e9 if bound == "hbm" else flops / t / 1e12
+        peak = peaks["hbm_gbs"] if bound == "hbm" else peaks["tflops"]
+        per_kernel[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": achieved / peak,
+                            "ms": kern_ms[name], "algorithmic_bytes": abytes[name], "flops": flops}
+    roof_time = sum(max(abytes[nm] / (peaks["hbm_gbs"] * 1e9), flops / (peaks["tflops"] * 1e12)) for nm in abytes)
+
+    # end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    y_host = torch.empty((n, cout), dtype=dtype).pin_memory()
+    gx_host = torch.empty((n, cin), dtype=dtype).pin_memory()
+    gw_host = torch.empty(tuple(w.shape), dtype=dtype).pin_memory()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        dyd = dy_host.to(dev, non_blocking=True)
+        y = cpp.gs_conv(xd, w, topo)
+        gx, gw = cpp.gs_conv_backward(dyd, xd, w, topo)
+        if world > 1:
+            dist.all_reduce(gw)
+        y_host.copy_(y, non_blocking=True)
+        gx_host.copy_(gx, non_blocking=True)
+        gw_host.copy_(gw, non_blocking=True)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(args.steps):
+        e2e_step()
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b) / args.steps
+
+    stats = torch.tensor([ms, e2e_ms, float(n), float(P)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_ms, total_n, total_p = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
+    else:
+        total_n, total_p = float(n), float(P)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, vox, pairs, threads = cpu_reference_step_time(cfg, 1, 2, 1)
+            cpu = {"value": vox / sec, "unit": "voxels/s", "cores": threads, "kind": "port",
+                   "sample": f"1 of {cfg['grids']} grids ({vox} voxels, {pairs} pairs) fwd+bwd fp32, median of 2 after 1 warm-up; oracle port of the GatherScatterDefault CPU path"}
+        roof = dict(per_kernel[dominant])
+        roof.update({"kernel": dominant, "traffic": None, "peak_source": peaks["source"]})
+        line = {
+            "metric": "sparse-conv voxels/sec fwd+bwd", "value": total_n / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
+            "data": "synthetic",
+            "config": {"workload": cfg["desc"], "grids_per_gpu": cfg["grids"], "voxels_per_gpu": n, "pairs_per_gpu": P, "pairs_per_voxel": P / max(n, 1),
+                       "kernel": f"{k}^3 stride 1 same-topology", "channels": f"{cin}->{cout}", "l2_policy": "inputs larger than L2 (features+grads+maps > 126 MB)",
+                       "collective": "all_reduce(grad_weights)" if world > 1 else "none", "plan_build_ms": plan_ms},
+            "voxel_features_per_s": total_n * (cin + cout) / 2 / (ms * 1e-3),
+            "roofline": roof, "roofline_kernels": per_kernel,
+            "roofline_step": {"roofline_ms": roof_time * 1e3, "measured_ms": fwd_ms + bwd_ms, "frac": roof_time * 1e3 / (fwd_ms + bwd_ms)},
+            "phase_ms": {"fwd": fwd_ms, "dgrad+wgrad": bwd_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total_n / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(x_host.numel() * s + dy_host.numel() * s), "d2h_bytes_per_step": int((y_host.numel() + gx_host.numel() + gw_host.numel()) * s)},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,357 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the fvdb mirror) against the CPU oracle and the
+golden vectors produced by the reference's own oracle.  Bit-exact for every integer product (grids, kernel
+maps, neighbour indices); fp64 1e-11 (the reference's own bar, test_conv_semantics_integration.py:214-242);
+fp32 1e-5 relative; f16/bf16 2e-2 against the fp32 oracle (north_star).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fvdb():
+    import fvdb as module
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return module
+
+
+DEV = "cuda"
+
+
+def _grid(fvdb, coords_per_grid, **kw):
+    tensors = [torch.tensor(np.asarray(c, dtype=np.int32).reshape(-1, 3), device=DEV) for c in coords_per_grid]
+    return fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(tensors), **kw)
+
+
+def _rows(grid):
+    return grid.ijk.jdata.cpu().numpy().astype(np.int64), grid.jidx.cpu().numpy().astype(np.int64)
+
+
+def _random_batch(seed, n=3000, extent=40, batches=3, dup=True):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(batches):
+        c = rng.integers(-extent, extent, size=(n, 3))
+        if dup:
+            c = np.concatenate([c, c[: n // 10]])
+        out.append(c)
+    return out
+
+
+def _canonical(gather, scatter, offsets):
+    """Sort every tap segment by (output row, feature row): the reference leaves pair order unspecified."""
+    gather, scatter = np.asarray(gather).astype(np.int64), np.asarray(scatter).astype(np.int64)
+    g2, s2 = gather.copy(), scatter.copy()
+    for k in range(len(offsets) - 1):
+        a, b = int(offsets[k]), int(offsets[k + 1])
+        order = np.lexsort((gather[a:b], scatter[a:b]))
+        g2[a:b], s2[a:b] = gather[a:b][order], scatter[a:b][order]
+    return g2, s2
+
+
+# ------------------------------------------------------------------ index grid
+
+
+def test_grid_build_rows_order_and_lookup(fvdb):
+    coords = _random_batch(1)
+    coords[1] = np.zeros((0, 3), dtype=np.int64)  # empty batch item is preserved
+    coords.append(np.array([[5000, -9000, 4096], [-4097, 0, 1], [2**20, -(2**20), 77], [5000, -9000, 4096]]))  # several root tiles
+    grid = _grid(fvdb, coords)
+    ijk, b = _rows(grid)
+    want = np.unique(np.concatenate([np.concatenate([np.full((len(c), 1), i), c], axis=1) for i, c in enumerate(coords)]), axis=0)
+    order = oracle.index_grid_row_order(want[:, 0], want[:, 1:])
+    assert grid.total_voxels == len(want) and grid.grid_count == 4
+    assert np.array_equal(b, want[order, 0]) and np.array_equal(ijk, want[order, 1:])  # bit-exact incl. row order
+    assert grid.joffsets.cpu().tolist() == np.concatenate([[0], np.cumsum(np.bincount(want[:, 0], minlength=4))]).tolist()
+    # ijk_to_index o ijk == identity (reference tests/unit/test_basic_ops.py), misses are -1
+    idx = grid.ijk_to_index(grid.ijk, cumulative=True).jdata.cpu().numpy()
+    assert np.array_equal(idx, np.arange(len(want)))
+    miss = fvdb.JaggedTensor([torch.tensor([[999, 999, 999]], dtype=torch.int32, device=DEV)] * 4)
+    assert grid.ijk_to_index(miss).jdata.cpu().tolist() == [-1] * 4
+    assert not bool(grid.coords_in_grid(miss).jdata.any())
+
+
+def test_neighbor_indexes_match_oracle(fvdb):
+    grid = _grid(fvdb, _random_batch(2, n=2000, extent=12))
+    ijk, b = _rows(grid)
+    offsets = grid.joffsets.cpu().numpy()
+    for extent, shift in ((1, 0), (2, 0), (1, 1)):
+        got = grid.neighbor_indexes(grid.ijk, extent, shift).jdata.cpu().numpy()
+        assert np.array_equal(got, oracle.neighbor_indexes(ijk, b, offsets, ijk, b, extent, shift))
+
+
+# ------------------------------------------------------------------ generated topologies + kernel maps
+
+_GEOMETRIES = [((k, k, k), (s, s, s)) for k in range(1, 7) for s in range(1, 6)] + [
+    ((2, 3, 4), (1, 2, 3)), ((5, 2, 3), (4, 2, 1)), ((3, 4, 2), (2, 3, 4)), ((3, 5, 7), (1, 1, 1)), ((7, 7, 7), (1, 1, 1)), ((1, 1, 1), (3, 2, 1))]
+
+
+@pytest.mark.parametrize("ks,st", _GEOMETRIES)
+def test_generated_grids_and_kernel_maps(fvdb, ks, st):
+    if ks == (1, 1, 1) and st == (1, 1, 1):
+        pytest.skip("identity geometry returns the same grid object")
+    coords = [[(-4, -1, 0), (-1, 0, 1), (0, 2, -3), (3, -2, 4), (5, 1, -1)], [], _random_batch(3, n=300, extent=9, batches=1)[0]]
+    fine = _grid(fvdb, coords)
+    f_ijk, f_b = _rows(fine)
+    coarse = fine.conv_grid(ks, st)
+    c_ijk, c_b = _rows(coarse)
+    want_ijk, want_b = oracle.conv_grid(f_ijk, f_b, ks, st)
+    order = oracle.index_grid_row_order(want_b, want_ijk)
+    assert np.array_equal(c_ijk, want_ijk[order]) and np.array_equal(c_b, want_b[order])
+    back = coarse.conv_transpose_grid(ks, st)
+    bk_ijk, bk_b = _rows(back)
+    want_ijk, want_b = oracle.conv_transpose_grid(c_ijk, c_b, ks, st)
+    order = oracle.index_grid_row_order(want_b, want_ijk)
+    assert np.array_equal(bk_ijk, want_ijk[order]) and np.array_equal(bk_b, want_b[order])
+    torch.testing.assert_close(coarse.voxel_sizes.cpu(), torch.tensor([st] * 3, dtype=torch.float32))
+    torch.testing.assert_close(back.voxel_sizes.cpu(), fine.voxel_sizes.cpu())
+
+    cpp = fvdb._fvdb_cpp
+    for transposed, (feat, out) in ((False, (fine, coarse)), (True, (coarse, fine))):
+        build = cpp.gs_build_transpose_topology if transposed else cpp.gs_build_topology
+        topo = build(feat.data, out.data, list(ks), list(st))
+        ref = oracle.build_topology(*_rows(feat), *_rows(out), ks, st, transposed=transposed)
+        assert topo.offsets.tolist() == ref.offsets.tolist() and topo.total_pairs == ref.total_pairs
+        assert topo.gather_indices.dtype == torch.int32 and topo.offsets.device.type == "cpu" and topo.is_transposed == transposed
+        g, s = _canonical(topo.gather_indices.cpu().numpy(), topo.scatter_indices.cpu().numpy(), ref.offsets)
+        rg, rs = _canonical(ref.gather_indices, ref.scatter_indices, ref.offsets)
+        assert np.array_equal(g, rg) and np.array_equal(s, rs)  # bit-exact kernel map
+        dense = topo._out_map().cpu().numpy()[:, : out.total_voxels].T
+        assert np.array_equal(dense, oracle.dense_kernel_map(*_rows(feat), *_rows(out), ks, st, transposed))
+        rev = cpp.gs_reverse_topology(topo)
+        assert rev.gather_indices.data_ptr() == topo.scatter_indices.data_ptr() and rev.is_transposed != transposed
+        want_rev = oracle.dense_kernel_map(*_rows(out), *_rows(feat), ks, st, not transposed)
+        assert np.array_equal(rev._out_map().cpu().numpy()[:, : feat.total_voxels].T, want_rev)
+
+
+def test_kernel_map_wide_neighbourhood_falls_back_to_tree_walk(fvdb):
+    # stride 5, kernel 6: the probe box of one output leaf spans > 128 source leaves -> per-probe tree walk path
+    fine = _grid(fvdb, [_random_batch(4, n=4000, extent=60, batches=1)[0]])
+    coarse = fine.conv_grid(6, 5)
+    topo = fvdb._fvdb_cpp.gs_build_topology(fine.data, coarse.data, [6] * 3, [5] * 3)
+    want = oracle.dense_kernel_map(*_rows(fine), *_rows(coarse), 6, 5)
+    assert np.array_equal(topo._out_map().cpu().numpy()[:, : coarse.total_voxels].T, want)
+
+
+# ------------------------------------------------------------------ values and gradients
+
+
+def test_golden_dense_values_and_gradients_fp64(fvdb, dense_golden):
+    data, meta = dense_golden
+    for case in meta:
+        key, ks, st, transposed = case["key"], case["kernel_size"], case["stride"], case["transposed"]
+        source = _grid(fvdb, [data[key + "_source"]])
+        factory = fvdb.ConvolutionPlan.from_grid_batch_transposed if transposed else fvdb.ConvolutionPlan.from_grid_batch
+        plan = factory(kernel_size=ks, stride=st, source_grid=source, acknowledge_incomplete_coverage=True)
+        src_rows = {tuple(r): i for i, r in enumerate(data[key + "_source"].tolist())}
+        tgt_rows = {tuple(r): i for i, r in enumerate(data[key + "_target"].tolist())}
+        src_perm = [src_rows[tuple(r)] for r in source.ijk.jdata.cpu().tolist()]
+        tgt_perm = [tgt_rows[tuple(r)] for r in plan.target_grid_batch.ijk.jdata.cpu().tolist()]
+        assert sorted(tgt_perm) == list(range(len(tgt_rows)))  # generated target == reference support
+        x = torch.from_numpy(data[key + "_features"])[src_perm].to(DEV).requires_grad_()
+        w = torch.from_numpy(data[key + "_weights"]).to(DEV).requires_grad_()
+        y = plan.execute(x, w)
+        torch.testing.assert_close(y.detach().cpu(), torch.from_numpy(data[key + "_values"])[tgt_perm], rtol=1e-11, atol=1e-11)
+        probe = torch.arange(1, y.numel() + 1, dtype=torch.float64).reshape(len(tgt_rows), -1)[tgt_perm].to(DEV)
+        gx, gw = torch.autograd.grad((y * probe).sum(), (x, w))
+        torch.testing.assert_close(gx.cpu(), torch.from_numpy(data[key + "_grad_features"])[src_perm], rtol=1e-11, atol=1e-11)
+        torch.testing.assert_close(gw.cpu(), torch.from_numpy(data[key + "_grad_weights"]), rtol=1e-11, atol=1e-11)
+
+
+def _oracle_run(plan_topology, x, w, dy):
+    topo = oracle.Topology(
+        plan_topology.gather_indices.cpu().numpy(), plan_topology.scatter_indices.cpu().numpy(), plan_topology.offsets.numpy(),
+        plan_topology.feature_total_voxels, plan_topology.output_total_voxels, plan_topology.kernel_volume, plan_topology.total_pairs,
+        tuple(plan_topology.kernel_size), tuple(plan_topology.stride), plan_topology.is_transposed)
+    y = oracle.gs_conv(x.float().cpu(), w.float().cpu(), topo, accumulate_dtype=torch.float32)
+    gx, gw = oracle.gs_conv_backward(dy.float().cpu(), x.float().cpu(), w.float().cpu(), topo, accumulate_dtype=torch.float32)
+    return y, gx, gw
+
+
+def _rel_err(got, want):
+    return float((got.float().cpu() - want).norm() / want.norm().clamp_min(1e-30))
+
+
+_VALUE_CASES = [
+    (torch.float32, 32, 32, 3, 1, 1e-5), (torch.float32, 4, 16, 3, 1, 1e-5), (torch.float32, 16, 48, (3, 5, 1), (1, 2, 1), 1e-5),
+    (torch.float32, 64, 64, 2, 2, 1e-5), (torch.float32, 128, 96, 3, 1, 1e-5), (torch.float32, 3, 5, 3, 1, 1e-5),
+    (torch.bfloat16, 64, 64, 3, 1, 2e-2), (torch.bfloat16, 32, 32, 3, 1, 2e-2), (torch.bfloat16, 16, 16, 5, 1, 2e-2),
+    (torch.bfloat16, 128, 128, 3, 1, 2e-2), (torch.bfloat16, 64, 128, 2, 2, 2e-2), (torch.bfloat16, 256, 256, 3, 1, 2e-2),
+    (torch.bfloat16, 64, 32, 3, 2, 2e-2), (torch.float16, 64, 64, 3, 1, 2e-2), (torch.float16, 32, 64, 3, 1, 2e-2),
+    (torch.bfloat16, 24, 40, 3, 1, 2e-2),
+]
+
+
+@pytest.mark.parametrize("dtype,cin,cout,ks,st,tol", _VALUE_CASES)
+@pytest.mark.parametrize("transposed", [False, True])
+def test_values_and_gradients_match_oracle(fvdb, dtype, cin, cout, ks, st, tol, transposed):
+    from fvdb.utils.synthetic import sphere_shell
+
+    shell = sphere_shell(target=6000, domain=64, seed=3, device="cpu").numpy()
+    source = _grid(fvdb, [shell, _random_batch(5, n=1500, extent=10, batches=1)[0]])
+    factory = fvdb.ConvolutionPlan.from_grid_batch_transposed if transposed else fvdb.ConvolutionPlan.from_grid_batch
+    same_topology = (not transposed) and oracle.normalize_3d(st) == (1, 1, 1)
+    plan = factory(kernel_size=ks, stride=st, source_grid=source, target_grid=source if same_topology else None, acknowledge_incomplete_coverage=True)
+    topo = plan._backend.topology
+    gen = torch.Generator().manual_seed(42)
+    k = oracle.normalize_3d(ks)
+    x = torch.randn((source.total_voxels, cin), generator=gen).to(dtype).to(DEV).requires_grad_()
+    bound = 1.0 / (cin * k[0] * k[1] * k[2]) ** 0.5
+    w = ((torch.rand((cout, cin, *k), generator=gen) * 2 - 1) * bound).to(dtype).to(DEV).requires_grad_()
+    dy = torch.randn((plan.target_grid_batch.total_voxels, cout), generator=gen).to(dtype).to(DEV)
+    y = plan.execute(source.jagged_like(x), w)
+    assert y.jdata.dtype == dtype and y.jdata.shape == (plan.target_grid_batch.total_voxels, cout)
+    gx, gw = torch.autograd.grad(y.jdata, (x, w), dy)
+    want_y, want_gx, want_gw = _oracle_run(topo, x.detach(), w.detach(), dy)
+    assert _rel_err(y.jdata.detach(), want_y) <= tol
+    assert _rel_err(gx, want_gx) <= tol
+    assert _rel_err(gw, want_gw) <= tol * (4 if dtype == torch.float32 else 1)  # reference widens kernel-grad tolerance (convolution_utils.py:119-131)
+    if dtype == torch.float32:  # elementwise too
+        torch.testing.assert_close(y.jdata.detach().cpu(), want_y, rtol=1e-4, atol=1e-5)
+
+
+def test_forced_cuda_core_path_for_half(fvdb):
+    cpp = fvdb._fvdb_cpp
+    source = _grid(fvdb, [_random_batch(6, n=2500, extent=9, batches=1)[0]])
+    plan = fvdb.ConvolutionPlan.from_grid_batch(3, 1, source, source)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn((source.total_voxels, 64), generator=gen).bfloat16().to(DEV)
+    w = (torch.randn((64, 64, 3, 3, 3), generator=gen) * 0.03).bfloat16().to(DEV)
+    dy = torch.randn((source.total_voxels, 64), generator=gen).bfloat16().to(DEV)
+    try:
+        cpp.set_conv_path("simt")
+        y = cpp.gs_conv(x, w, plan._backend.topology)
+        gx, gw = cpp.gs_conv_backward(dy, x, w, plan._backend.topology)
+    finally:
+        cpp.set_conv_path("auto")
+    want_y, want_gx, want_gw = _oracle_run(plan._backend.topology, x, w, dy)
+    assert _rel_err(y, want_y) <= 2e-2 and _rel_err(gx, want_gx) <= 2e-2 and _rel_err(gw, want_gw) <= 2e-2
+
+
+def test_all_ones_equals_rulebook_degree_and_adjoint(fvdb):
+    # size-independent properties on a larger grid: all-ones => degree (test_conv_semantics_integration.py:149-168);
+    # weighted adjoint <y, d> == <x, L^T d> through from_plan_transposed (:903-947)
+    from fvdb.utils.synthetic import indoor_room
+
+    source = _grid(fvdb, [indoor_room(target=60_000, seed=s, device="cpu").numpy() for s in (0, 1)])
+    plan = fvdb.ConvolutionPlan.from_grid_batch(3, 2, source, acknowledge_incomplete_coverage=True)
+    ones = plan.execute(source.jagged_like(torch.ones((source.total_voxels, 1), dtype=torch.float64, device=DEV)), torch.ones((1, 1, 3, 3, 3), dtype=torch.float64, device=DEV))
+    degree = torch.bincount(plan._backend.topology.scatter_indices, minlength=plan.target_grid_batch.total_voxels)
+    assert torch.equal(ones.jdata[:, 0], degree.double()) and int(degree.min()) >= 1
+    report = plan.coverage_report
+    assert report.output_zero_count == 0 and report.input_row_count == source.total_voxels
+    gen = torch.Generator().manual_seed(50)
+    x = torch.randn((source.total_voxels, 8), generator=gen, dtype=torch.float64).to(DEV)
+    w = torch.randn((16, 8, 3, 3, 3), generator=gen, dtype=torch.float64).to(DEV)
+    d = torch.randn((plan.target_grid_batch.total_voxels, 16), generator=gen, dtype=torch.float64).to(DEV)
+    y = plan.execute(source.jagged_like(x), w).jdata
+    adj = fvdb.ConvolutionPlan.from_plan_transposed(plan)
+    assert adj.topology_provenance is fvdb.ConvolutionTopologyProvenance.EXACT_TRANSPOSE
+    lt_d = adj.execute(plan.target_grid_batch.jagged_like(d), w.transpose(0, 1).contiguous()).jdata
+    torch.testing.assert_close((y * d).sum(), (x * lt_d).sum(), rtol=1e-12, atol=1e-8)
+
+
+def test_flip_identity_and_determinism(fvdb):
+    source = _grid(fvdb, [_random_batch(7, n=4000, extent=12, batches=1)[0]])
+    fwd = fvdb.ConvolutionPlan.from_grid_batch(3, 1, source, source)
+    tr = fvdb.ConvolutionPlan.from_grid_batch_transposed(3, 1, source, source)
+    gen = torch.Generator().manual_seed(70)
+    x = torch.randn((source.total_voxels, 8), generator=gen, dtype=torch.float64).to(DEV)
+    w = torch.randn((8, 8, 3, 3, 3), generator=gen, dtype=torch.float64).to(DEV)
+    torch.testing.assert_close(tr.execute(x, w), fwd.execute(x, w.flip(2, 3, 4)), rtol=1e-12, atol=1e-12)
+    xb, wb = x.bfloat16(), (w * 0.05).bfloat16()
+    assert torch.equal(fwd.execute(xb, wb), fwd.execute(xb, wb))  # no atomics on the output-stationary path
+    dy = torch.randn_like(xb)
+    g1 = fvdb._fvdb_cpp.gs_conv_backward(dy, xb, wb, fwd._backend.topology)
+    g2 = fvdb._fvdb_cpp.gs_conv_backward(dy, xb, wb, fwd._backend.topology)
+    assert torch.equal(g1[0], g2[0]) and torch.equal(g1[1], g2[1])
+
+
+# ------------------------------------------------------------------ plan / module behaviour
+
+
+def test_plan_api_contract(fvdb):
+    Plan = fvdb.ConvolutionPlan
+    fine = _grid(fvdb, [[(0, 0, 0)]], voxel_sizes=(0.5, 1.0, 2.0), origins=(3.0, -2.0, 7.0))
+    plan = Plan.from_grid_batch(kernel_size=(4, 3, 2), stride=1, source_grid=fine)
+    assert plan.geometry.kernel_size == [4, 3, 2] and plan.geometry.padding_before == [1, 1, 0] and plan.geometry.padding_after == [2, 1, 1]
+    assert plan.geometry.kernel_volume == 24 and plan.geometry.semantics_version == 1 and plan.geometry.phase_policy == "torch_same_phase"
+    assert plan.phase_policy is fvdb.ConvolutionPhasePolicy.TORCH_SAME_PHASE and plan.transform_compatibility.compatible
+    strided = Plan.from_grid_batch(kernel_size=3, stride=2, source_grid=fine)
+    torch.testing.assert_close(strided.target_grid_batch.voxel_sizes.cpu(), torch.tensor([[1.0, 2.0, 4.0]]))
+    torch.testing.assert_close(strided.target_grid_batch.origins.cpu(), fine.origins.cpu())
+    unit = _grid(fvdb, [[(0, 0, 0)]])
+    with pytest.raises(ValueError, match="nonzero integer.*a=0"):
+        Plan.from_grid_batch(3, 2, unit, _grid(fvdb, [[(0, 0, 0)]], voxel_sizes=2.0, origins=(1.0, 0.0, 0.0)))
+    with pytest.raises(ValueError, match="fractional.*a=0"):
+        Plan.from_grid_batch(3, 2, unit, _grid(fvdb, [[(0, 0, 0)]], voxel_sizes=2.0, origins=(0.5, 0.0, 0.0)))
+    with pytest.raises(ValueError, match="voxel size"):
+        Plan.from_grid_batch(3, 2, unit, unit)
+    with pytest.raises(ValueError, match="same batch size"):
+        Plan.from_grid_batch(3, 1, unit, _grid(fvdb, [[(0, 0, 0)], [(1, 1, 1)]]))
+    with pytest.raises(ValueError, match="COMPLETE.*target_grid=None"):
+        Plan.from_grid_batch(3, 1, unit, unit, topology_policy=fvdb.ConvolutionTopologyPolicy.COMPLETE)
+    with pytest.raises(ValueError, match="RESTRICTED.*explicit target_grid"):
+        Plan.from_grid_batch(3, 1, unit, topology_policy=fvdb.ConvolutionTopologyPolicy.RESTRICTED)
+    with pytest.raises(ValueError, match="dense convolution backend is disabled"):
+        Plan.from_grid_batch(3, 1, unit, expert_config={"backend": "dense"})
+    with pytest.raises(ValueError, match="uniform kernel sizes 3, 5, 7"):
+        Plan.from_grid_batch(4, 1, unit, expert_config={"backend": "pred_gather_igemm"})
+    with pytest.raises(ValueError, match="channel counts divisible by 32"):
+        Plan.from_grid_batch(3, 1, unit, expert_config={"backend": "pred_gather_igemm"}, channel_pairs=((8, 32),))
+    with pytest.raises(ValueError, match="does not support transposed convolution"):
+        Plan.from_grid_batch_transposed(3, 1, unit, expert_config={"backend": "pred_gather_igemm"})
+    far = _grid(fvdb, [[(100, 100, 100)]])
+    with pytest.raises(ValueError, match="zero-degree output"):
+        Plan.from_grid_batch(3, 1, unit, far, strict_output_coverage=True)
+    assert Plan.from_grid_batch(3, 1, unit, far).execute(torch.ones(1, 2, device=DEV), torch.ones(3, 2, 3, 3, 3, device=DEV)).abs().sum() == 0
+    with pytest.warns(fvdb.ConvolutionCoverageWarning, match="uncovered stride residues"):
+        Plan.from_grid_batch(1, 2, _grid(fvdb, [[(0, 0, 0), (1, 1, 1)]]))
+    # K = S = 1 on the same grid object is a matmul; equal-looking distinct grids go through the map
+    ident = Plan.from_grid_batch(1, 1, unit)
+    assert type(ident._backend).__name__ == "_MatmulBackend" and unit.conv_grid(1, 1) is unit
+    assert type(Plan.from_grid_batch(1, 1, unit, _grid(fvdb, [[(0, 0, 0)]]))._backend).__name__ == "_GatherScatterBackend"
+    x = torch.randn(1, 4, device=DEV)
+    w2 = torch.randn(6, 4, device=DEV)
+    torch.testing.assert_close(ident.execute(x, w2), x @ w2.T)
+    with pytest.raises(ValueError, match="batch size of 1"):
+        Plan.from_grid_batch(3, 1, _grid(fvdb, [[(0, 0, 0)], [(1, 1, 1)]])).execute(torch.ones(2, 2, device=DEV), torch.ones(2, 2, 3, 3, 3, device=DEV))
+    with pytest.raises(ValueError, match="not supported"):
+        Plan.from_grid_batch(3, 1, unit, channel_pairs=((2, 4),)).execute(torch.ones(1, 2, device=DEV), torch.ones(3, 2, 3, 3, 3, device=DEV))
+    topo = Plan.from_grid_batch(3, 1, unit)._backend.topology
+    with pytest.raises(RuntimeError, match="requires topology with direction=Transposed"):
+        fvdb._fvdb_cpp.gs_conv_transpose(torch.ones(1, 2, device=DEV), torch.ones(3, 2, 3, 3, 3, device=DEV), topo)
+    with pytest.raises(RuntimeError, match="features.size\\(0\\)"):
+        fvdb._fvdb_cpp.gs_conv(torch.ones(5, 2, device=DEV), torch.ones(3, 2, 3, 3, 3, device=DEV), topo)
+    with pytest.raises(RuntimeError, match="kernel_size"):
+        fvdb._fvdb_cpp.gs_conv(torch.ones(1, 2, device=DEV), torch.ones(3, 2, 5, 3, 3, device=DEV), topo)
+    # dtype promotion table (GatherScatterDefaultConvTest.cu:1712-1786)
+    assert fvdb._fvdb_cpp.gs_conv(torch.ones(1, 2, device=DEV, dtype=torch.bfloat16), torch.ones(3, 2, 3, 3, 3, device=DEV), topo).dtype == torch.float32
+    assert fvdb._fvdb_cpp.gs_conv(torch.ones(1, 2, device=DEV), torch.ones(3, 2, 3, 3, 3, device=DEV, dtype=torch.float64), topo).dtype == torch.float64
+
+
+def test_nn_modules_train_step(fvdb):
+    source = _grid(fvdb, [_random_batch(8, n=2000, extent=10, batches=1)[0], _random_batch(9, n=1000, extent=8, batches=1)[0]])
+    down = fvdb.ConvolutionPlan.from_grid_batch(2, 2, source)
+    same = fvdb.ConvolutionPlan.from_grid_batch(3, 1, source, source)
+    up = fvdb.ConvolutionPlan.from_plan_transposed(down)
+    conv = fvdb.nn.SparseConv3d(8, 16, 3).to(DEV)
+    pool = fvdb.nn.SparseConv3d(16, 32, 2, 2, bias=False).to(DEV)
+    unpool = fvdb.nn.SparseConvTranspose3d(32, 8, 2, 2).to(DEV)
+    assert conv.weight.shape == (16, 8, 3, 3, 3) and not conv.weight.is_contiguous()
+    x = source.jagged_like(torch.randn(source.total_voxels, 8, device=DEV))
+    out = unpool(pool(conv(x, same), down), up)
+    assert out.jdata.shape == (source.total_voxels, 8) and torch.isfinite(out.jdata).all()
+    out.jdata.square().mean().backward()
+    for p in list(conv.parameters()) + list(pool.parameters()) + list(unpool.parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
+    with pytest.raises(ValueError, match="mismatched"):
+        conv(x, down)
+    # strided (non-contiguous) nn weights give the same result as a contiguous copy
+    torch.testing.assert_close(same.execute(x, conv.weight).jdata, same.execute(x, conv.weight.detach().contiguous()).jdata)
