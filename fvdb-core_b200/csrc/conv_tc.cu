@@ -1,11 +1,314 @@
-// conv_tc.cu -- tcgen05 / TMEM implicit-GEMM path (placeholder while the CUDA-core path is validated).
+// conv_tc.cu -- tcgen05 / TMEM implicit-GEMM sparse convolution for f16 / bf16 (fp32 accumulate).
+//
+// Replaces PredGatherIGemm.cu (SM80 mma.sync TF32, forward only, one CTA per leaf) and the cuBLAS
+// gather -> mm -> atomic-scatter pipeline of GatherScatterDefault.cu:706-721,786-808 for the half types.
+//
+// Forward / dgrad kernel (output-stationary, no atomics):
+//   a CTA owns TILES consecutive 128-row output tiles; their fp32 accumulators (128 lanes x COUT columns
+//   each) stay in TMEM for the whole tap loop.  For every (tap, 64-channel block) the weight chunk
+//   B = W[tap][:, block] (COUT x 64, K-major, 128B-swizzled image prepared by tc_pack_b_kernel) arrives by
+//   ONE cp.async.bulk; then for each tile the 4 producer warps gather the 128 neighbour rows (128 B each)
+//   with 16-byte zero-filling cp.async straight into the canonical K-major SWIZZLE_128B layout, and one
+//   elected thread issues 4 x tcgen05.mma (M=128, N=COUT, K=16) accumulating into that tile's TMEM slice.
+//   Stages are recycled by tcgen05.commit -> mbarrier.  Epilogue: tcgen05.ld -> (+bias) -> bf16/f16 -> one
+//   plain 128-bit store stream per output row.
+//
+// Warp roles (192 threads): warps 0-3 gather producers, then epilogue (warp w owns TMEM lanes 32w..32w+31);
+// warp 4 TMEM allocator + MMA issuer; warp 5 weight-chunk loader.
 #include "conv_internal.cuh"
+#include "tc_ptx.cuh"
 
 namespace fvc {
-bool tc_forward_supported(int32_t, int32_t, int64_t, int32_t) { return false; }
-size_t tc_forward_scratch_bytes(int64_t, int32_t, int32_t, int64_t, int32_t) { return 0; }
-int tc_forward(const ConvArgs &) { return set_error(FVC_ERR_UNSUPPORTED, "tensor-core path not built"); }
+
+using namespace tc;
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_TILE_M = 128;
+constexpr int TC_A_BYTES = TC_TILE_M * 128; // one stage: 128 rows x 64 channels x 2 B
+constexpr int TC_LAG = 3;                   // cp.async groups in flight per producer thread before signalling
+
+constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int CIN, int COUT, int TILES, int STAGES> struct TcFwdCfg {
+    static constexpr int KB = CIN / 64;                      // 64-channel reduction blocks per tap
+    static constexpr int B_BYTES = COUT * 128;               // one weight chunk: COUT rows x 64 channels x 2 B
+    static constexpr int TMEM_COLS = tmem_cols_for(TILES * COUT);
+    static constexpr int CTAS_PER_SM = TMEM_COLS <= 256 ? 2 : 1;
+    static constexpr int NUM_BARS = 2 * STAGES + 5;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + 2 * size_t(B_BYTES) + 8 * NUM_BARS + 16;
+    static_assert(CIN % 64 == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
+    static_assert(TILES * COUT <= 512, "accumulators exceed TMEM");
+    static_assert(STAGES > TC_LAG, "pipeline must be deeper than the signalling lag");
+};
+
+// Weight image: for chunk c = tap * KB + j, COUT rows of 128 B; row n holds channels [64j, 64j+64) of
+// W[tap][:, n] with 16-byte chunk q stored at position q ^ (n & 7)  (the SWIZZLE_128B K-major atom).
+__global__ void tc_pack_b_kernel(const uint16_t *__restrict__ w /*[k3][cin][cout]*/, int k3, int cin, int cout,
+                                 uint4 *__restrict__ img) {
+    const int kb = cin / 64;
+    const int64_t total = int64_t(k3) * kb * cout * 8; // 16-byte chunks
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+        const int pos = int(e & 7);
+        const int n = int((e >> 3) % cout);
+        const int64_t chunk = (e >> 3) / cout;
+        const int j = int(chunk % kb), tap = int(chunk / kb);
+        const int q = pos ^ (n & 7);
+        const uint16_t *src = w + (int64_t(tap) * cin + j * 64 + q * 8) * cout + n;
+        uint32_t v[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            v[h] = uint32_t(src[int64_t(2 * h) * cout]) | (uint32_t(src[int64_t(2 * h + 1) * cout]) << 16);
+        img[e] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b, bool bf16) {
+    if (bf16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float half_to_float(uint16_t v, bool bf16) {
+    return bf16 ? __bfloat162float(*reinterpret_cast<__nv_bfloat16 *>(&v)) : __half2float(*reinterpret_cast<__half *>(&v));
+}
+
+template <int CIN, int COUT, int TILES, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, (TcFwdCfg<CIN, COUT, TILES, STAGES>::CTAS_PER_SM))
+conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_img, const uint16_t *__restrict__ bias,
+                   uint16_t *__restrict__ y, const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int k3, uint32_t idesc,
+                   int is_bf16) {
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES>;
+    constexpr int KB = Cfg::KB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
+    const uint32_t bars = smem_b + 2 * Cfg::B_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
+    const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
+    const uint32_t bar_accum = bar_bempty + 16;
+    const uint32_t tmem_slot = bar_accum + 8;
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total_tiles = (n_out + TC_TILE_M - 1) / TC_TILE_M;
+    const int64_t tile0 = int64_t(blockIdx.x) * TILES;
+    const int ntiles = int(total_tiles - tile0 < TILES ? total_tiles - tile0 : TILES);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 128); // one arrival per producer thread
+            mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_bfull + 8 * b, 1); // expect_tx arrival + bytes
+            mbar_init(bar_bempty + 8 * b, 1);
+        }
+        mbar_init(bar_accum, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4)
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < 4) {
+        // ================= gather producers =================
+        const int r = threadIdx.x; // this thread fetches the map entry of tile row r
+        auto load_idx = [&](int k, int t) -> int {
+            const int64_t row = (tile0 + t) * TC_TILE_M + r;
+            return row < n_out ? __ldg(nbr + int64_t(k) * pitch + row) : -1;
+        };
+        int u = 0;
+        int idx_next = load_idx(0, 0);
+        for (int k = 0; k < k3; ++k) {
+            for (int j = 0; j < KB; ++j) {
+                for (int t = 0; t < ntiles; ++t, ++u) {
+                    const int idx = idx_next;
+                    { // prefetch the next unit's map entry
+                        int t2 = t + 1, j2 = j, k2 = k;
+                        if (t2 == ntiles) {
+                            t2 = 0;
+                            if (++j2 == KB) {
+                                j2 = 0;
+                                ++k2;
+                            }
+                        }
+                        idx_next = k2 < k3 ? load_idx(k2, t2) : -1;
+                    }
+                    const int s = u % STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
+                    const uint32_t stage = smem_a + s * TC_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { // 8 lanes cover one 128-byte row; 4 rows per warp instruction
+                        const int rl = 4 * i + (lane >> 3);
+                        const int row = warp * 32 + rl, q = lane & 7;
+                        const int src_idx = __shfl_sync(0xffffffffu, idx, rl);
+                        const uint16_t *src = x + (src_idx >= 0 ? int64_t(src_idx) * CIN + j * 64 + q * 8 : 0);
+                        cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
+                    }
+                    cp_async_commit();
+                    if (u >= TC_LAG) {
+                        cp_async_wait<TC_LAG>();
+                        fence_proxy_async();
+                        mbar_arrive(bar_full + 8 * ((u - TC_LAG) % STAGES));
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int v = (u > TC_LAG ? u - TC_LAG : 0); v < u; ++v)
+            mbar_arrive(bar_full + 8 * (v % STAGES));
+
+        // ================= epilogue =================
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const bool bf16 = is_bf16 != 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int64_t row = (tile0 + t) * TC_TILE_M + warp * 32 + lane;
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(t * COUT + c0), acc);
+                tmem_ld_wait();
+                if (row < n_out) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(y + row * COUT + c0);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        uint32_t p[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            float a = __uint_as_float(acc[v4 * 8 + 2 * h]), b = __uint_as_float(acc[v4 * 8 + 2 * h + 1]);
+                            if (bias) {
+                                a += half_to_float(bias[c0 + v4 * 8 + 2 * h], bf16);
+                                b += half_to_float(bias[c0 + v4 * 8 + 2 * h + 1], bf16);
+                            }
+                            p[h] = pack_half2(a, b, bf16);
+                        }
+                        dst[v4] = make_uint4(p[0], p[1], p[2], p[3]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            int u = 0;
+            for (int k = 0; k < k3; ++k) {
+                for (int j = 0; j < KB; ++j) {
+                    const int c = k * KB + j, b = c & 1;
+                    mbar_wait(bar_bfull + 8 * b, (c >> 1) & 1);
+                    const uint32_t b_base = smem_b + b * Cfg::B_BYTES;
+                    for (int t = 0; t < ntiles; ++t, ++u) {
+                        const int s = u % STAGES;
+                        mbar_wait(bar_full + 8 * s, (u / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_a + s * TC_A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) // 4 x K=16 inside the 128-byte swizzle span
+                            umma_f16(tmem_base + uint32_t(t * COUT), make_smem_desc_sw128(a_base + kk * 32, 16, 1024),
+                                     make_smem_desc_sw128(b_base + kk * 32, 16, 1024), idesc, (c | kk) != 0 ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * s); // stage reusable once these MMAs retire
+                    }
+                    umma_commit(bar_bempty + 8 * b);
+                }
+            }
+            umma_commit(bar_accum);
+        }
+        __syncwarp();
+    } else {
+        // ================= weight-chunk loader (one thread) =================
+        if (lane == 0) {
+            const int chunks = k3 * KB;
+            for (int c = 0; c < chunks; ++c) {
+                const int b = c & 1;
+                mbar_wait(bar_bempty + 8 * b, ((c >> 1) & 1) ^ 1);
+                mbar_expect_tx(bar_bfull + 8 * b, Cfg::B_BYTES);
+                bulk_g2s(smem_b + b * Cfg::B_BYTES, w_img + int64_t(c) * Cfg::B_BYTES, Cfg::B_BYTES, bar_bfull + 8 * b);
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4)
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+template <int CIN, int COUT, int TILES, int STAGES> static int launch_tc_fwd(const ConvArgs &a, const uint8_t *w_img) {
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES>;
+    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES>;
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
+        configured = true;
+    }
+    const int64_t tiles = ceil_div(a.n_out, TC_TILE_M);
+    const unsigned grid = unsigned(ceil_div(tiles, TILES));
+    const bool bf16 = a.dtype == FVC_BF16;
+    const uint32_t idesc = make_idesc_f16(TC_TILE_M, COUT, bf16, false, false);
+    kernel<<<grid, TC_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), w_img,
+                                                      reinterpret_cast<const uint16_t *>(a.bias), reinterpret_cast<uint16_t *>(a.y),
+                                                      a.nbr, a.pitch, a.n_out, a.k3, idesc, bf16 ? 1 : 0);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
+    if (dtype != FVC_F16 && dtype != FVC_BF16)
+        return false;
+    if (k3 < 1 || k3 > 4096)
+        return false;
+    const bool cin_ok = cin == 64 || cin == 128 || cin == 256;
+    const bool cout_ok = cout == 32 || cout == 64 || cout == 128 || cout == 256;
+    return cin_ok && cout_ok;
+}
+
+size_t tc_forward_scratch_bytes(int64_t, int32_t cin, int32_t cout, int64_t k3, int32_t) {
+    return size_t(k3) * size_t(cin) * size_t(cout) * 2 + 256;
+}
+
+int tc_forward(const ConvArgs &a) {
+    const size_t need = tc_forward_scratch_bytes(a.n_out, a.cin, a.cout, a.k3, a.dtype);
+    FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core conv scratch too small: %zu < %zu",
+                a.scratch_bytes, need);
+    FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0,
+                FVC_ERR_RUNTIME, "tensor-core conv needs 16-byte aligned feature / output / scratch pointers");
+    uint8_t *img = reinterpret_cast<uint8_t *>(a.scratch);
+    const int64_t chunks16 = int64_t(a.k3) * a.cin * a.cout / 8;
+    tc_pack_b_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
+        reinterpret_cast<const uint16_t *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
+    FVC_LAUNCH_CHECK();
+#define FVC_TC_CASE(CI, CO, T, S)    \
+    if (a.cin == CI && a.cout == CO) \
+        return launch_tc_fwd<CI, CO, T, S>(a, img);
+    FVC_TC_CASE(64, 32, 8, 5)
+    FVC_TC_CASE(64, 64, 4, 5)
+    FVC_TC_CASE(64, 128, 4, 8)
+    FVC_TC_CASE(64, 256, 2, 8)
+    FVC_TC_CASE(128, 32, 8, 5)
+    FVC_TC_CASE(128, 64, 4, 5)
+    FVC_TC_CASE(128, 128, 4, 8)
+    FVC_TC_CASE(128, 256, 2, 8)
+    FVC_TC_CASE(256, 32, 8, 5)
+    FVC_TC_CASE(256, 64, 4, 5)
+    FVC_TC_CASE(256, 128, 4, 8)
+    FVC_TC_CASE(256, 256, 2, 8)
+#undef FVC_TC_CASE
+    return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core kernel for channels %d -> %d", a.cin, a.cout);
+}
+
+// tensor-core weight gradient: not built yet (the CUDA-core CSR kernel serves wgrad)
 bool tc_wgrad_supported(int32_t, int32_t, int64_t, int32_t) { return false; }
 size_t tc_wgrad_scratch_bytes(int64_t, int32_t, int32_t, int64_t, int32_t) { return 0; }
-int tc_wgrad(const WgradArgs &) { return set_error(FVC_ERR_UNSUPPORTED, "tensor-core path not built"); }
+int tc_wgrad(const WgradArgs &) { return set_error(FVC_ERR_UNSUPPORTED, "tensor-core wgrad not built"); }
+
 } // namespace fvc

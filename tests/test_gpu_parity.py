@@ -355,3 +355,25 @@ def test_nn_modules_train_step(fvdb):
         conv(x, down)
     # strided (non-contiguous) nn weights give the same result as a contiguous copy
     torch.testing.assert_close(same.execute(x, conv.weight).jdata, same.execute(x, conv.weight.detach().contiguous()).jdata)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 32), (256, 64)])
+def test_tensor_core_identity_map_is_plain_gemm(fvdb, cin, cout):
+    # K^3 = 1 on two equal-looking but distinct grids: the kernel map is the identity, so the tcgen05 kernel
+    # must reproduce x @ W^T -- isolates UMMA descriptors / swizzle / TMEM epilogue from the gather logic.
+    cpp = fvdb._fvdb_cpp
+    coords = _random_batch(11, n=700, extent=6, batches=1, dup=False)[0]
+    a, b = _grid(fvdb, [coords]), _grid(fvdb, [coords])
+    topo = cpp.gs_build_topology(a.data, b.data, [1, 1, 1], [1, 1, 1])
+    assert topo.total_pairs == a.total_voxels
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn((a.total_voxels, cin), generator=gen).bfloat16().to(DEV)
+    w = (torch.randn((cout, cin, 1, 1, 1), generator=gen) / cin**0.5).bfloat16().to(DEV)
+    try:
+        cpp.set_conv_path("tc")
+        y = cpp.gs_conv(x, w, topo)
+    finally:
+        cpp.set_conv_path("auto")
+    want = x.float() @ w[:, :, 0, 0, 0].float().T
+    assert _rel_err(y, want.cpu()) <= 1e-2
+    torch.testing.assert_close(y.float(), want, rtol=2e-2, atol=2e-2)
