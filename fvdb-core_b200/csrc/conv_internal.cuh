@@ -41,6 +41,9 @@ struct WgradArgs {
 int simt_forward(const ConvArgs &a);
 size_t simt_wgrad_scratch_bytes(int64_t total_pairs_max_tap, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
 int simt_wgrad(const WgradArgs &a);
+// grad_w[co][ci][k] = sum over chunks of partial[chunk][k][ci][co] (fixed order), cast to `dtype`
+int wgrad_reduce_partials(const void *partial, int nchunks, int32_t cin, int32_t cout, int32_t k3, int32_t dtype, void *grad_w,
+                          cudaStream_t stream);
 
 // tcgen05 path: f16/bf16, channel counts the UMMA tile shapes admit
 bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);

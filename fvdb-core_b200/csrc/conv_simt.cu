@@ -245,12 +245,29 @@ template <typename T> static int launch_wgrad(const WgradArgs &a) {
         reinterpret_cast<const T *>(a.x), reinterpret_cast<const T *>(a.dy), a.gather, a.scatter, a.offsets_dev, a.cin, a.cout,
         a.k3, chunk, partial);
     FVC_LAUNCH_CHECK();
-    const int64_t per_chunk = int64_t(a.k3) * a.cin * a.cout;
+    return wgrad_reduce_partials(partial, int(nchunks), a.cin, a.cout, a.k3, a.dtype, a.grad_w, a.stream);
+}
+
+template <typename T>
+static int launch_reduce(const void *partial, int nchunks, int32_t cin, int32_t cout, int32_t k3, void *grad_w, cudaStream_t stream) {
+    using A = typename AccOf<T>::type;
+    const int64_t per_chunk = int64_t(k3) * cin * cout;
     const int blocks = int(ceil_div(per_chunk, 256) > 148 * 8 ? 148 * 8 : ceil_div(per_chunk, 256));
-    wgrad_reduce_kernel<T><<<blocks, 256, 0, a.stream>>>(partial, int(nchunks), a.cin, a.cout, a.k3,
-                                                         reinterpret_cast<T *>(a.grad_w));
+    wgrad_reduce_kernel<T><<<blocks, 256, 0, stream>>>(reinterpret_cast<const A *>(partial), nchunks, cin, cout, k3,
+                                                       reinterpret_cast<T *>(grad_w));
     FVC_LAUNCH_CHECK();
     return FVC_OK;
+}
+
+int wgrad_reduce_partials(const void *partial, int nchunks, int32_t cin, int32_t cout, int32_t k3, int32_t dtype, void *grad_w,
+                          cudaStream_t stream) {
+    switch (dtype) {
+    case FVC_F16: return launch_reduce<__half>(partial, nchunks, cin, cout, k3, grad_w, stream);
+    case FVC_BF16: return launch_reduce<__nv_bfloat16>(partial, nchunks, cin, cout, k3, grad_w, stream);
+    case FVC_F32: return launch_reduce<float>(partial, nchunks, cin, cout, k3, grad_w, stream);
+    case FVC_F64: return launch_reduce<double>(partial, nchunks, cin, cout, k3, grad_w, stream);
+    default: return set_error(FVC_ERR_UNSUPPORTED, "no weight-gradient reduction for dtype code %d", dtype);
+    }
 }
 
 int simt_wgrad(const WgradArgs &a) {

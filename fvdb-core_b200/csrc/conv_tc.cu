@@ -25,7 +25,6 @@ using namespace tc;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TILE_M = 128;
 constexpr int TC_A_BYTES = TC_TILE_M * 128; // one stage: 128 rows x 64 channels x 2 B
-constexpr int TC_LAG = 3;                   // cp.async groups in flight per producer thread before signalling
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -38,7 +37,6 @@ template <int CIN, int COUT, int TILES, int STAGES> struct TcFwdCfg {
     static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + 2 * size_t(B_BYTES) + 8 * NUM_BARS + 16;
     static_assert(CIN % 64 == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * COUT <= 512, "accumulators exceed TMEM");
-    static_assert(STAGES > TC_LAG, "pipeline must be deeper than the signalling lag");
 };
 
 // Weight image: for chunk c = tap * KB + j, COUT rows of 128 B; row n holds channels [64j, 64j+64) of
@@ -152,19 +150,13 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                         const uint16_t *src = x + (src_idx >= 0 ? int64_t(src_idx) * CIN + j * 64 + q * 8 : 0);
                         cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
                     }
-                    cp_async_commit();
-                    if (u >= TC_LAG) {
-                        cp_async_wait<TC_LAG>();
-                        fence_proxy_async();
-                        mbar_arrive(bar_full + 8 * ((u - TC_LAG) % STAGES));
-                    }
+                    // completion-triggered arrival (the CUTLASS sm100 cp.async -> UMMA idiom): the producer never
+                    // blocks on its own loads, so up to STAGES gathers per CTA stay in flight
+                    cp_async_arrive_noinc(bar_full + 8 * s);
                 }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (int v = (u > TC_LAG ? u - TC_LAG : 0); v < u; ++v)
-            mbar_arrive(bar_full + 8 * (v % STAGES));
+        cp_async_wait_all();
 
         // ================= epilogue =================
         mbar_wait(bar_accum, 0);
@@ -306,9 +298,6 @@ int tc_forward(const ConvArgs &a) {
     return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core kernel for channels %d -> %d", a.cin, a.cout);
 }
 
-// tensor-core weight gradient: not built yet (the CUDA-core CSR kernel serves wgrad)
-bool tc_wgrad_supported(int32_t, int32_t, int64_t, int32_t) { return false; }
-size_t tc_wgrad_scratch_bytes(int64_t, int32_t, int32_t, int64_t, int32_t) { return 0; }
-int tc_wgrad(const WgradArgs &) { return set_error(FVC_ERR_UNSUPPORTED, "tensor-core wgrad not built"); }
+// tensor-core weight gradient: conv_tc_wgrad.cu
 
 } // namespace fvc

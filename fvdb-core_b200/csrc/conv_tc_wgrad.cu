@@ -1,0 +1,267 @@
+// conv_tc_wgrad.cu -- tcgen05 / TMEM weight gradient for f16 / bf16 (fp32 accumulate, fixed-order reduction).
+//
+//   dW[k][ci][co] = sum over output rows o of  X[nbr[k][o]][ci] * dY[o][co]        (GatherScatterDefault.cu:806-807)
+//
+// Output-stationary over the dense tap-major map, like the forward kernel, but with the roles of the GEMM
+// dimensions rotated: the REDUCTION runs over output rows (K = 128 rows per tile, 8 x tcgen05.mma of K=16),
+// M stacks (tap, input channel) and N is the output channel.  Both operands are therefore MN-major:
+//   A = gathered X rows   [128 rows][64 ch]  -- exactly the 128B-swizzled block the forward producers write,
+//   B = the dY tile       [128 rows][64 ch]  -- loaded once per tile and shared by every tap.
+// An "M-unit" is two such A blocks (M = 128 = two taps x 64 channels when Cin = 64, or two channel blocks of
+// one tap when Cin = 128 ...), its accumulator is 128 TMEM lanes x Cout columns and stays resident while
+// the CTA streams over its share of the row tiles.  TMEM (512 columns) holds 512 / Cout units, so the
+// taps are split into groups (grid.y) and the rows into chunks (grid.x); every CTA writes one fp32 partial
+// [K^3][Cin][Cout] slice that wgrad_reduce_partials sums in a fixed order (deterministic, no atomics).
+#include "conv_internal.cuh"
+#include "tc_ptx.cuh"
+
+namespace fvc {
+
+using namespace tc;
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_TILE = 128;
+constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 channels x 2 B
+
+template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
+    static constexpr int CB = CIN / 64;            // A channel blocks per tap
+    static constexpr int NB = COUT / 64;           // B channel blocks
+    static constexpr int MAX_UNITS = 512 / COUT;   // accumulators that fit TMEM
+    static constexpr int A_STAGE = 2 * WG_BLOCK_BYTES;
+    static constexpr int B_STAGE = NB * WG_BLOCK_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 5;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + 2 * size_t(B_STAGE) + 8 * NUM_BARS + 16;
+    static_assert(CIN % 64 == 0 && COUT % 64 == 0 && CIN <= 256 && COUT <= 256, "unsupported channel counts");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+};
+
+// 128 rows x 128 B into one swizzled block; 8 lanes cover one row (one full 128-byte line), 4 rows per instruction
+__device__ __forceinline__ void gather_block(uint32_t block_smem, const uint16_t *__restrict__ base, int64_t row_stride,
+                                             int col0, int idx, int warp, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = 4 * i + (lane >> 3);
+        const int row = warp * 32 + rl, q = lane & 7;
+        const int src_idx = __shfl_sync(0xffffffffu, idx, rl);
+        const uint16_t *src = base + (src_idx >= 0 ? int64_t(src_idx) * row_stride + col0 + q * 8 : 0);
+        cp_async16(block_smem + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
+    }
+}
+
+template <int CIN, int COUT, int STAGES>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
+                     int64_t pitch, int64_t n_out, int k3, int units_per_group, int tiles_per_chunk, uint32_t idesc,
+                     float *__restrict__ partial) {
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES>;
+    constexpr int CB = Cfg::CB, NB = Cfg::NB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + STAGES * Cfg::A_STAGE;
+    const uint32_t bars = smem_b + 2 * Cfg::B_STAGE;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
+    const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
+    const uint32_t bar_accum = bar_bempty + 16;
+    const uint32_t tmem_slot = bar_accum + 8;
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_blocks = k3 * CB;
+    const int total_units = (total_blocks + 1) / 2;
+    const int unit0 = blockIdx.y * units_per_group;
+    const int nunits = total_units - unit0 < units_per_group ? total_units - unit0 : units_per_group;
+    const int64_t total_tiles = (n_out + WG_TILE - 1) / WG_TILE;
+    const int64_t tile_begin = int64_t(blockIdx.x) * tiles_per_chunk;
+    const int64_t tile_end = tile_begin + tiles_per_chunk < total_tiles ? tile_begin + tiles_per_chunk : total_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 128);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_bfull + 8 * b, 128);
+            mbar_init(bar_bempty + 8 * b, 1);
+        }
+        mbar_init(bar_accum, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4)
+        tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < 4) {
+        // ================= producers: dY tile, then the gathered X blocks of every unit =================
+        const int r = threadIdx.x;
+        auto tap_idx = [&](int block, int64_t row) -> int { // map entry for A block `block` (tap = block / CB)
+            return (block < total_blocks && row < n_out) ? __ldg(nbr + int64_t(block / CB) * pitch + row) : -1;
+        };
+        int u = 0, tb = 0;
+        for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+            const int64_t row = tile * WG_TILE + r;
+            int idx0 = tap_idx(2 * unit0, row), idx1 = tap_idx(2 * unit0 + 1, row);
+            { // B: plain rows of dY (identity "map")
+                const int bs = tb & 1;
+                mbar_wait(bar_bempty + 8 * bs, ((tb >> 1) & 1) ^ 1);
+                const int self = row < n_out ? int(row) : -1;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+                    gather_block(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES, dy, COUT, nb * 64, self, warp, lane);
+                cp_async_arrive_noinc(bar_bfull + 8 * bs);
+            }
+            for (int ul = 0; ul < nunits; ++ul, ++u) {
+                const int blk = 2 * (unit0 + ul);
+                const int cur0 = idx0, cur1 = idx1;
+                if (ul + 1 < nunits) { // prefetch the next unit's map entries
+                    idx0 = tap_idx(blk + 2, row);
+                    idx1 = tap_idx(blk + 3, row);
+                }
+                const int s = u % STAGES;
+                mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
+                const uint32_t stage = smem_a + s * Cfg::A_STAGE;
+                gather_block(stage, x, CIN, (blk % CB) * 64, cur0, warp, lane);
+                gather_block(stage + WG_BLOCK_BYTES, x, CIN, ((blk + 1) % CB) * 64, cur1, warp, lane);
+                cp_async_arrive_noinc(bar_full + 8 * s);
+            }
+        }
+        cp_async_wait_all();
+
+        // ================= epilogue: accumulators -> fp32 partial slice =================
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const int half = warp >> 1;                       // which A block of the unit this warp's lanes belong to
+        const int ci_local = (warp & 1) * 32 + lane;      // channel inside the block
+        float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
+        for (int ul = 0; ul < nunits; ++ul) {
+            const int blk = 2 * (unit0 + ul) + half;
+            const bool live = blk < total_blocks;
+            const int tap = blk / CB, ci = (blk % CB) * 64 + ci_local;
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * COUT + c0), acc);
+                tmem_ld_wait();
+                if (live) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(slice + (int64_t(tap) * CIN + ci) * COUT + c0);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        dst[v] = make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int u = 0, tb = 0;
+            for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+                const int bs = tb & 1;
+                mbar_wait(bar_bfull + 8 * bs, (tb >> 1) & 1);
+                const uint32_t b_base = smem_b + bs * Cfg::B_STAGE;
+                for (int ul = 0; ul < nunits; ++ul, ++u) {
+                    const int s = u % STAGES;
+                    mbar_wait(bar_full + 8 * s, (u / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_a + s * Cfg::A_STAGE;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) // 16 rows (K) per MMA = two 8-row swizzle groups = 2048 B
+                        umma_f16(tmem_base + uint32_t(ul * COUT),
+                                 make_smem_desc_sw128(a_base + kk * 2048, WG_BLOCK_BYTES, 1024),
+                                 make_smem_desc_sw128(b_base + kk * 2048, WG_BLOCK_BYTES, 1024), idesc,
+                                 (tb | kk) != 0 ? 1u : 0u);
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_bempty + 8 * bs);
+            }
+            umma_commit(bar_accum);
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4)
+        tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct WgradPlan {
+    int groups, units_per_group, chunks, tiles_per_chunk;
+};
+
+static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3) {
+    WgradPlan p;
+    const int total_units = (k3 * (cin / 64) + 1) / 2;
+    const int max_units = 512 / cout;
+    p.groups = int(ceil_div(total_units, max_units));
+    p.units_per_group = int(ceil_div(total_units, p.groups)); // balanced groups
+    const int64_t tiles = ceil_div(n_out, WG_TILE);
+    int64_t chunks = 148 / p.groups; // one CTA per SM (TMEM: 512 columns each)
+    if (chunks < 1)
+        chunks = 1;
+    if (chunks > tiles)
+        chunks = tiles;
+    p.tiles_per_chunk = int(ceil_div(tiles, chunks));
+    p.chunks = int(ceil_div(tiles, p.tiles_per_chunk));
+    return p;
+}
+
+template <int CIN, int COUT, int STAGES> static int launch_tc_wgrad(const WgradArgs &a) {
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES>;
+    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
+        configured = true;
+    }
+    const WgradPlan p = plan_wgrad(a.n_out, CIN, COUT, a.k3);
+    const uint32_t idesc = make_idesc_f16(128, COUT, a.dtype == FVC_BF16, true, true);
+    float *partial = reinterpret_cast<float *>(a.scratch);
+    dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
+    kernel<<<grid, WG_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), reinterpret_cast<const uint16_t *>(a.dy),
+                                                      a.nbr, a.pitch, a.n_out, a.k3, p.units_per_group, p.tiles_per_chunk, idesc, partial);
+    FVC_LAUNCH_CHECK();
+    return wgrad_reduce_partials(partial, p.chunks, a.cin, a.cout, a.k3, a.dtype, a.grad_w, a.stream);
+}
+
+bool tc_wgrad_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
+    if (dtype != FVC_F16 && dtype != FVC_BF16)
+        return false;
+    if (k3 < 1 || k3 > 4096)
+        return false;
+    const bool ok = (cin == 64 || cin == 128 || cin == 256) && (cout == 64 || cout == 128 || cout == 256);
+    return ok;
+}
+
+size_t tc_wgrad_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t) {
+    const WgradPlan p = plan_wgrad(n_out > 0 ? n_out : 1, cin, cout, int(k3));
+    return size_t(p.chunks) * size_t(k3) * size_t(cin) * size_t(cout) * 4 + 256;
+}
+
+int tc_wgrad(const WgradArgs &a) {
+    const size_t need = tc_wgrad_scratch_bytes(a.n_out, a.cin, a.cout, a.k3, a.dtype);
+    FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core wgrad scratch too small: %zu < %zu",
+                a.scratch_bytes, need);
+    FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0,
+                FVC_ERR_RUNTIME, "tensor-core wgrad needs 16-byte aligned pointers");
+#define FVC_WG_CASE(CI, CO, S)       \
+    if (a.cin == CI && a.cout == CO) \
+        return launch_tc_wgrad<CI, CO, S>(a);
+    FVC_WG_CASE(64, 64, 4)
+    FVC_WG_CASE(64, 128, 4)
+    FVC_WG_CASE(64, 256, 3)
+    FVC_WG_CASE(128, 64, 4)
+    FVC_WG_CASE(128, 128, 4)
+    FVC_WG_CASE(128, 256, 3)
+    FVC_WG_CASE(256, 64, 4)
+    FVC_WG_CASE(256, 128, 4)
+    FVC_WG_CASE(256, 256, 3)
+#undef FVC_WG_CASE
+    return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core wgrad kernel for channels %d -> %d", a.cin, a.cout);
+}
+
+} // namespace fvc
