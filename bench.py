@@ -265,8 +265,8 @@ def run_ours(args, cfg):
     w_bwd = cpp._pack_weights(w, dtype, 1)
     out_map, in_map = topo._out_map(), topo._in_map()
     kern_ms = {
-        "fwd": timed(lambda: cpp._run_conv(x, w_fwd, out_map, n, n, cin, cout, k3), max(3, args.steps)),
-        "dgrad": timed(lambda: cpp._run_conv(dy, w_bwd, in_map, n, n, cout, cin, k3), max(3, args.steps)),
+        "fwd": timed(lambda: cpp._run_conv(x, w_fwd, out_map, n, n, cin, cout, k3, None, topo._out_mask()), max(3, args.steps)),
+        "dgrad": timed(lambda: cpp._run_conv(dy, w_bwd, in_map, n, n, cout, cin, k3, None, topo._in_mask()), max(3, args.steps)),
     }
     kern_ms["wgrad"] = max(bwd_ms - kern_ms["dgrad"], 1e-6)
     peaks = load_peaks()

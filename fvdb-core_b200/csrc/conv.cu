@@ -23,7 +23,7 @@ size_t fvc_conv_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t 
 }
 
 int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
-                     int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                     const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                      int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream) {
     int rc = check_common(x, w_packed, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_forward");
     if (rc)
@@ -34,7 +34,7 @@ int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void
     FVC_REQUIRE(y && (kernel_volume == 0 || nbr), FVC_ERR_RUNTIME, "fvc_conv_forward: null output / map pointer");
     FVC_REQUIRE(pitch >= n_out, FVC_ERR_RUNTIME, "fvc_conv_forward: map pitch %lld < output rows %lld", (long long)pitch,
                 (long long)n_out);
-    ConvArgs a{x, w_packed, bias, y, nbr, pitch, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype, scratch, scratch_bytes,
+    ConvArgs a{x, w_packed, bias, y, nbr, pitch, tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype, scratch, scratch_bytes,
                reinterpret_cast<cudaStream_t>(stream)};
     const bool tc_ok = tc_forward_supported(cin, cout, kernel_volume, dtype);
     if (path == 2 && !tc_ok)
@@ -53,7 +53,7 @@ size_t fvc_conv_wgrad_scratch_bytes(int64_t n_out, int64_t total_pairs, int32_t 
 
 int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const int32_t *scatter,
                    const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
-                   int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                   const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                    int32_t path, void *grad_w, void *scratch, size_t scratch_bytes, fvc_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_common(x, dy, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_wgrad");
@@ -70,7 +70,7 @@ int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const i
         return FVC_OK;
     }
     FVC_REQUIRE(gather && scatter && offsets_dev, FVC_ERR_RUNTIME, "fvc_conv_wgrad: null CSR pointer");
-    WgradArgs a{x, dy, gather, scatter, offsets_host, offsets_dev, nbr, pitch, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype,
+    WgradArgs a{x, dy, gather, scatter, offsets_host, offsets_dev, nbr, pitch, tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype,
                 grad_w, scratch, scratch_bytes, stream};
     const bool tc_ok = nbr && tc_wgrad_supported(cin, cout, kernel_volume, dtype);
     if (path == 2 && !tc_ok)

@@ -11,6 +11,7 @@ struct ConvArgs {
     void *y;
     const int32_t *nbr; // tap-major dense map
     int64_t pitch;
+    const uint64_t *tile_mask; // per 128-row tile tap bitmask (may be null)
     int64_t n_in, n_out;
     int32_t cin, cout;
     int32_t k3;
@@ -27,6 +28,7 @@ struct WgradArgs {
     const int64_t *offsets_host, *offsets_dev;
     const int32_t *nbr;
     int64_t pitch;
+    const uint64_t *tile_mask;
     int64_t n_in, n_out;
     int32_t cin, cout;
     int32_t k3;

@@ -25,6 +25,7 @@ using namespace tc;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TILE_M = 128;
 constexpr int TC_A_BYTES = TC_TILE_M * 128; // one stage: 128 rows x 64 channels x 2 B
+constexpr int TC_MASK_WORDS = 8;            // tile tap-mask words kept in shared memory (K^3 <= 512)
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -75,8 +76,8 @@ __device__ __forceinline__ float half_to_float(uint16_t v, bool bf16) {
 template <int CIN, int COUT, int TILES, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, (TcFwdCfg<CIN, COUT, TILES, STAGES>::CTAS_PER_SM))
 conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_img, const uint16_t *__restrict__ bias,
-                   uint16_t *__restrict__ y, const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int k3, uint32_t idesc,
-                   int is_bf16) {
+                   uint16_t *__restrict__ y, const int32_t *__restrict__ nbr, int64_t pitch,
+                   const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, uint32_t idesc, int is_bf16) {
     using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES>;
     constexpr int KB = Cfg::KB;
     extern __shared__ uint8_t smem_raw[];
@@ -95,6 +96,26 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const int64_t total_tiles = (n_out + TC_TILE_M - 1) / TC_TILE_M;
     const int64_t tile0 = int64_t(blockIdx.x) * TILES;
     const int ntiles = int(total_tiles - tile0 < TILES ? total_tiles - tile0 : TILES);
+
+    // tap bitmask of every tile this CTA owns: (tile, tap) units without a single valid row are skipped by all roles
+    __shared__ unsigned long long s_tmask[TILES][TC_MASK_WORDS];
+    {
+        const int words = (k3 + 63) >> 6;
+        for (int i = threadIdx.x; i < TILES * TC_MASK_WORDS; i += TC_THREADS) {
+            const int t = i / TC_MASK_WORDS, w = i % TC_MASK_WORDS;
+            unsigned long long m = 0ull;
+            if (t < ntiles && w < words)
+                m = tile_mask ? __ldg(tile_mask + (tile0 + t) * words + w) : ~0ull;
+            s_tmask[t][w] = m;
+        }
+    }
+    auto active = [&](int k, int t) -> bool { return (s_tmask[t][k >> 6] >> (k & 63)) & 1ull; };
+    auto tap_any = [&](int k) -> bool {
+        unsigned long long any = 0ull;
+        for (int t = 0; t < ntiles; ++t)
+            any |= s_tmask[t][k >> 6];
+        return (any >> (k & 63)) & 1ull;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -122,39 +143,40 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             const int64_t row = (tile0 + t) * TC_TILE_M + r;
             return row < n_out ? __ldg(nbr + int64_t(k) * pitch + row) : -1;
         };
-        int u = 0;
-        int idx_next = load_idx(0, 0);
-        for (int k = 0; k < k3; ++k) {
-            for (int j = 0; j < KB; ++j) {
-                for (int t = 0; t < ntiles; ++t, ++u) {
-                    const int idx = idx_next;
-                    { // prefetch the next unit's map entry
-                        int t2 = t + 1, j2 = j, k2 = k;
-                        if (t2 == ntiles) {
-                            t2 = 0;
-                            if (++j2 == KB) {
-                                j2 = 0;
-                                ++k2;
-                            }
-                        }
-                        idx_next = k2 < k3 ? load_idx(k2, t2) : -1;
+        // walk the active (tap, channel block, tile) units; the map entry of the NEXT active unit is fetched while
+        // the current one is being issued, so the L2 latency of the index load stays off the critical path
+        auto advance = [&](int &k, int &j, int &t) {
+            do {
+                if (++t == ntiles) {
+                    t = 0;
+                    if (++j == KB) {
+                        j = 0;
+                        ++k;
                     }
-                    const int s = u % STAGES;
-                    mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
-                    const uint32_t stage = smem_a + s * TC_A_BYTES;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { // 8 lanes cover one 128-byte row; 4 rows per warp instruction
-                        const int rl = 4 * i + (lane >> 3);
-                        const int row = warp * 32 + rl, q = lane & 7;
-                        const int src_idx = __shfl_sync(0xffffffffu, idx, rl);
-                        const uint16_t *src = x + (src_idx >= 0 ? int64_t(src_idx) * CIN + j * 64 + q * 8 : 0);
-                        cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
-                    }
-                    // completion-triggered arrival (the CUTLASS sm100 cp.async -> UMMA idiom): the producer never
-                    // blocks on its own loads, so up to STAGES gathers per CTA stay in flight
-                    cp_async_arrive_noinc(bar_full + 8 * s);
                 }
+            } while (k < k3 && !active(k, t));
+        };
+        int k = 0, j = 0, t = -1;
+        advance(k, j, t);
+        int idx_next = k < k3 ? load_idx(k, t) : -1;
+        for (int u = 0; k < k3; ++u) {
+            const int idx = idx_next, jc = j;
+            advance(k, j, t);
+            idx_next = k < k3 ? load_idx(k, t) : -1;
+            const int s = u % STAGES;
+            mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
+            const uint32_t stage = smem_a + s * TC_A_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { // 8 lanes cover one 128-byte row; 4 rows per warp instruction
+                const int rl = 4 * i + (lane >> 3);
+                const int row = warp * 32 + rl, q = lane & 7;
+                const int src_idx = __shfl_sync(0xffffffffu, idx, rl);
+                const uint16_t *src = x + (src_idx >= 0 ? int64_t(src_idx) * CIN + jc * 64 + q * 8 : 0);
+                cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
             }
+            // completion-triggered arrival (the CUTLASS sm100 cp.async -> UMMA idiom): the producer never
+            // blocks on its own loads, so up to STAGES gathers per CTA stay in flight
+            cp_async_arrive_noinc(bar_full + 8 * s);
         }
         cp_async_wait_all();
 
@@ -164,11 +186,20 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         const bool bf16 = is_bf16 != 0;
         for (int t = 0; t < ntiles; ++t) {
             const int64_t row = (tile0 + t) * TC_TILE_M + warp * 32 + lane;
+            unsigned long long live = 0ull; // a tile no tap reaches was never accumulated: its rows are zero
+            for (int w = 0; w < TC_MASK_WORDS; ++w)
+                live |= s_tmask[t][w];
 #pragma unroll
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t acc[32];
-                tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(t * COUT + c0), acc);
-                tmem_ld_wait();
+                if (live) {
+                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(t * COUT + c0), acc);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        acc[e] = 0u;
+                }
                 if (row < n_out) {
                     uint4 *dst = reinterpret_cast<uint4 *>(y + row * COUT + c0);
 #pragma unroll
@@ -191,22 +222,30 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     } else if (warp == 4) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            int u = 0;
+            int u = 0, c = 0;
+            uint32_t started = 0; // tiles whose accumulator has been written at least once
             for (int k = 0; k < k3; ++k) {
-                for (int j = 0; j < KB; ++j) {
-                    const int c = k * KB + j, b = c & 1;
+                if (!tap_any(k))
+                    continue;
+                for (int j = 0; j < KB; ++j, ++c) {
+                    const int b = c & 1;
                     mbar_wait(bar_bfull + 8 * b, (c >> 1) & 1);
                     const uint32_t b_base = smem_b + b * Cfg::B_BYTES;
-                    for (int t = 0; t < ntiles; ++t, ++u) {
+                    for (int t = 0; t < ntiles; ++t) {
+                        if (!active(k, t))
+                            continue;
                         const int s = u % STAGES;
                         mbar_wait(bar_full + 8 * s, (u / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t a_base = smem_a + s * TC_A_BYTES;
+                        const uint32_t acc0 = (started >> t) & 1u;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) // 4 x K=16 inside the 128-byte swizzle span
                             umma_f16(tmem_base + uint32_t(t * COUT), make_smem_desc_sw128(a_base + kk * 32, 16, 1024),
-                                     make_smem_desc_sw128(b_base + kk * 32, 16, 1024), idesc, (c | kk) != 0 ? 1u : 0u);
+                                     make_smem_desc_sw128(b_base + kk * 32, 16, 1024), idesc, (acc0 | uint32_t(kk != 0)));
                         umma_commit(bar_empty + 8 * s); // stage reusable once these MMAs retire
+                        started |= 1u << t;
+                        ++u;
                     }
                     umma_commit(bar_bempty + 8 * b);
                 }
@@ -217,12 +256,16 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     } else {
         // ================= weight-chunk loader (one thread) =================
         if (lane == 0) {
-            const int chunks = k3 * KB;
-            for (int c = 0; c < chunks; ++c) {
-                const int b = c & 1;
-                mbar_wait(bar_bempty + 8 * b, ((c >> 1) & 1) ^ 1);
-                mbar_expect_tx(bar_bfull + 8 * b, Cfg::B_BYTES);
-                bulk_g2s(smem_b + b * Cfg::B_BYTES, w_img + int64_t(c) * Cfg::B_BYTES, Cfg::B_BYTES, bar_bfull + 8 * b);
+            int c = 0;
+            for (int k = 0; k < k3; ++k) {
+                if (!tap_any(k))
+                    continue;
+                for (int j = 0; j < KB; ++j, ++c) {
+                    const int b = c & 1;
+                    mbar_wait(bar_bempty + 8 * b, ((c >> 1) & 1) ^ 1);
+                    mbar_expect_tx(bar_bfull + 8 * b, Cfg::B_BYTES);
+                    bulk_g2s(smem_b + b * Cfg::B_BYTES, w_img + int64_t(k * KB + j) * Cfg::B_BYTES, Cfg::B_BYTES, bar_bfull + 8 * b);
+                }
             }
         }
         __syncwarp();
@@ -248,7 +291,8 @@ template <int CIN, int COUT, int TILES, int STAGES> static int launch_tc_fwd(con
     const uint32_t idesc = make_idesc_f16(TC_TILE_M, COUT, bf16, false, false);
     kernel<<<grid, TC_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), w_img,
                                                       reinterpret_cast<const uint16_t *>(a.bias), reinterpret_cast<uint16_t *>(a.y),
-                                                      a.nbr, a.pitch, a.n_out, a.k3, idesc, bf16 ? 1 : 0);
+                                                      a.nbr, a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out,
+                                                      a.k3, idesc, bf16 ? 1 : 0);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }
@@ -256,7 +300,7 @@ template <int CIN, int COUT, int TILES, int STAGES> static int launch_tc_fwd(con
 bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
     if (dtype != FVC_F16 && dtype != FVC_BF16)
         return false;
-    if (k3 < 1 || k3 > 4096)
+    if (k3 < 1 || k3 > 64 * TC_MASK_WORDS)
         return false;
     const bool cin_ok = cin == 64 || cin == 128 || cin == 256;
     const bool cout_ok = cout == 32 || cout == 64 || cout == 128 || cout == 256;

@@ -51,8 +51,8 @@ __device__ __forceinline__ void gather_block(uint32_t block_smem, const uint16_t
 template <int CIN, int COUT, int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
-                     int64_t pitch, int64_t n_out, int k3, int units_per_group, int tiles_per_chunk, uint32_t idesc,
-                     float *__restrict__ partial) {
+                     int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
+                     int tiles_per_chunk, uint32_t idesc, float *__restrict__ partial) {
     using Cfg = TcWgradCfg<CIN, COUT, STAGES>;
     constexpr int CB = Cfg::CB, NB = Cfg::NB;
     extern __shared__ uint8_t smem_raw[];
@@ -64,6 +64,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
     const uint32_t bar_accum = bar_bempty + 16;
     const uint32_t tmem_slot = bar_accum + 8;
+    __shared__ uint32_t s_started; // units whose accumulator was written at least once (MMA thread -> epilogue)
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + (tmem_slot - smem_base));
 
@@ -76,7 +77,25 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     const int64_t tile_begin = int64_t(blockIdx.x) * tiles_per_chunk;
     const int64_t tile_end = tile_begin + tiles_per_chunk < total_tiles ? tile_begin + tiles_per_chunk : total_tiles;
 
+    // (tile, unit) skipping: a unit is live for a tile iff one of its (at most two) taps reaches a row of the tile.
+    // Both roles evaluate the same predicate from the tile's tap bitmask (K^3 <= 128; larger kernels do not skip).
+    const int words = (k3 + 63) >> 6;
+    const bool use_mask = tile_mask != nullptr && words <= 2;
+    auto unit_live = [&](unsigned long long m0, unsigned long long m1, int ul) -> bool {
+        if (!use_mask)
+            return true;
+        const int blk = 2 * (unit0 + ul);
+        const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
+        const unsigned long long bit_a = ((ta < 64 ? m0 : m1) >> (ta & 63)) & 1ull;
+        const unsigned long long bit_b = ((tb_ < 64 ? m0 : m1) >> (tb_ & 63)) & 1ull;
+        return (bit_a | bit_b) != 0ull;
+    };
+    auto load_mask = [&](int64_t tile, int w) -> unsigned long long {
+        return (use_mask && w < words) ? __ldg(tile_mask + tile * words + w) : 0ull;
+    };
+
     if (threadIdx.x == 0) {
+        s_started = 0u;
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 128);
             mbar_init(bar_empty + 8 * s, 1);
@@ -104,7 +123,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         int u = 0, tb = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
             const int64_t row = tile * WG_TILE + r;
-            int idx0 = tap_idx(2 * unit0, row), idx1 = tap_idx(2 * unit0 + 1, row);
+            const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
             { // B: plain rows of dY (identity "map")
                 const int bs = tb & 1;
                 mbar_wait(bar_bempty + 8 * bs, ((tb >> 1) & 1) ^ 1);
@@ -114,12 +133,24 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     gather_block(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES, dy, COUT, nb * 64, self, warp, lane);
                 cp_async_arrive_noinc(bar_bfull + 8 * bs);
             }
-            for (int ul = 0; ul < nunits; ++ul, ++u) {
+            // live units of this tile; the NEXT live unit's map entries are fetched while the current one is issued
+            int ul = 0;
+            while (ul < nunits && !unit_live(m0, m1, ul))
+                ++ul;
+            int idx0 = -1, idx1 = -1;
+            if (ul < nunits) {
+                idx0 = tap_idx(2 * (unit0 + ul), row);
+                idx1 = tap_idx(2 * (unit0 + ul) + 1, row);
+            }
+            for (; ul < nunits; ++u) {
                 const int blk = 2 * (unit0 + ul);
                 const int cur0 = idx0, cur1 = idx1;
-                if (ul + 1 < nunits) { // prefetch the next unit's map entries
-                    idx0 = tap_idx(blk + 2, row);
-                    idx1 = tap_idx(blk + 3, row);
+                do {
+                    ++ul;
+                } while (ul < nunits && !unit_live(m0, m1, ul));
+                if (ul < nunits) {
+                    idx0 = tap_idx(2 * (unit0 + ul), row);
+                    idx1 = tap_idx(2 * (unit0 + ul) + 1, row);
                 }
                 const int s = u % STAGES;
                 mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
@@ -134,6 +165,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         // ================= epilogue: accumulators -> fp32 partial slice =================
         mbar_wait(bar_accum, 0);
         tc_fence_after();
+        const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started);
         const int half = warp >> 1;                       // which A block of the unit this warp's lanes belong to
         const int ci_local = (warp & 1) * 32 + lane;      // channel inside the block
         float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
@@ -144,8 +176,14 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
 #pragma unroll
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t acc[32];
-                tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * COUT + c0), acc);
-                tmem_ld_wait();
+                if ((started >> ul) & 1u) {
+                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * COUT + c0), acc);
+                    tmem_ld_wait();
+                } else { // no row of this CTA's tiles ever reached these taps
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        acc[e] = 0u;
+                }
                 if (live) {
                     uint4 *dst = reinterpret_cast<uint4 *>(slice + (int64_t(tap) * CIN + ci) * COUT + c0);
 #pragma unroll
@@ -158,11 +196,15 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         // ================= MMA issuer =================
         if (lane == 0) {
             int u = 0, tb = 0;
+            uint32_t started = 0;
             for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
                 const int bs = tb & 1;
+                const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
                 mbar_wait(bar_bfull + 8 * bs, (tb >> 1) & 1);
                 const uint32_t b_base = smem_b + bs * Cfg::B_STAGE;
-                for (int ul = 0; ul < nunits; ++ul, ++u) {
+                for (int ul = 0; ul < nunits; ++ul) {
+                    if (!unit_live(m0, m1, ul))
+                        continue;
                     const int s = u % STAGES;
                     mbar_wait(bar_full + 8 * s, (u / STAGES) & 1);
                     tc_fence_after();
@@ -172,11 +214,15 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                         umma_f16(tmem_base + uint32_t(ul * COUT),
                                  make_smem_desc_sw128(a_base + kk * 2048, WG_BLOCK_BYTES, 1024),
                                  make_smem_desc_sw128(b_base + kk * 2048, WG_BLOCK_BYTES, 1024), idesc,
-                                 (tb | kk) != 0 ? 1u : 0u);
+                                 ((started >> ul) & 1u) | uint32_t(kk != 0));
                     umma_commit(bar_empty + 8 * s);
+                    started |= 1u << ul;
+                    ++u;
                 }
                 umma_commit(bar_bempty + 8 * bs);
             }
+            *reinterpret_cast<volatile uint32_t *>(&s_started) = started;
+            __threadfence_block();
             umma_commit(bar_accum);
         }
         __syncwarp();
@@ -222,7 +268,8 @@ template <int CIN, int COUT, int STAGES> static int launch_tc_wgrad(const WgradA
     float *partial = reinterpret_cast<float *>(a.scratch);
     dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
     kernel<<<grid, WG_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), reinterpret_cast<const uint16_t *>(a.dy),
-                                                      a.nbr, a.pitch, a.n_out, a.k3, p.units_per_group, p.tiles_per_chunk, idesc, partial);
+                                                      a.nbr, a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out,
+                                                      a.k3, p.units_per_group, p.tiles_per_chunk, idesc, partial);
     FVC_LAUNCH_CHECK();
     return wgrad_reduce_partials(partial, p.chunks, a.cin, a.cout, a.k3, a.dtype, a.grad_w, a.stream);
 }

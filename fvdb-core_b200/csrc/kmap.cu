@@ -246,6 +246,25 @@ __global__ void degree_kernel(const int32_t *__restrict__ nbr, int64_t pitch, in
     }
 }
 
+// one CTA per 128-row tile; bit k of the tile's mask = "some row of the tile has a neighbour through tap k"
+__global__ void __launch_bounds__(128)
+tile_mask_kernel(const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int k3, int words,
+                 unsigned long long *__restrict__ mask) {
+    extern __shared__ unsigned long long s_words[];
+    for (int w = threadIdx.x; w < words; w += blockDim.x)
+        s_words[w] = 0ull;
+    __syncthreads();
+    const int64_t row = int64_t(blockIdx.x) * 128 + threadIdx.x;
+    for (int k = 0; k < k3; ++k) {
+        const bool valid = row < n_out && nbr[int64_t(k) * pitch + row] >= 0;
+        if (__ballot_sync(0xffffffffu, valid) != 0u && (threadIdx.x & 31) == 0)
+            atomicOr(&s_words[k >> 6], 1ull << (k & 63));
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < words; w += blockDim.x)
+        mask[int64_t(blockIdx.x) * words + w] = s_words[w];
+}
+
 // ---- lookups --------------------------------------------------------------------------------------
 __global__ void neighbor_indexes_kernel(FvcGridBatch grid, const int32_t *__restrict__ q_ijk,
                                         const int32_t *__restrict__ q_bidx, int64_t nq, int extent, int shift,
@@ -446,6 +465,19 @@ int fvc_kmap_reverse_dense(const int32_t *gather, const int32_t *scatter, const 
         return FVC_OK;
     reverse_dense_kernel<<<grid_for(total_pairs, 256), 256, 0, stream>>>(gather, scatter, offsets_dev, int(kernel_volume),
                                                                          total_pairs, nbr_rev, pitch_rev);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_kmap_tile_mask(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, uint64_t *mask,
+                       fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_out == 0 || kernel_volume == 0)
+        return FVC_OK;
+    FVC_REQUIRE(kernel_volume <= 4096, FVC_ERR_UNSUPPORTED, "kernel volume %lld exceeds the tile-mask limit 4096", (long long)kernel_volume);
+    const int words = int((kernel_volume + 63) / 64);
+    tile_mask_kernel<<<unsigned(ceil_div(n_out, 128)), 128, words * 8, stream>>>(nbr, pitch, n_out, int(kernel_volume), words,
+                                                                                reinterpret_cast<unsigned long long *>(mask));
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }

@@ -247,6 +247,17 @@ def ijk_to_index(grid: GridBatchData, ijk: torch.Tensor, jidx: "torch.Tensor | N
 # ---------------------------------------------------------------------------------------------
 
 
+def _tile_mask(nbr: torch.Tensor, rows: int, kernel_volume: int) -> "torch.Tensor | None":
+    """Per 128-row tile tap bitmask of a dense map (fvc_kmap_tile_mask); lets the executors skip empty units."""
+    if rows == 0 or kernel_volume == 0 or kernel_volume > 4096:
+        return None
+    words = (kernel_volume + 63) // 64
+    mask = torch.empty(((rows + 127) // 128) * words, dtype=torch.int64, device=nbr.device)
+    with torch.cuda.device(nbr.device):
+        check(lib.fvc_kmap_tile_mask(_ptr(nbr), int(nbr.shape[1]), rows, kernel_volume, mask.data_ptr(), _stream(nbr.device)))
+    return mask
+
+
 class _MapCore:
     """Storage shared by a topology and its constant-time reversed view.
 
@@ -258,8 +269,9 @@ class _MapCore:
     def __init__(self, gather, scatter, offsets_host, offsets_dev, nbr, n_feature, n_output, kernel_volume):
         self.gather, self.scatter = gather, scatter
         self.offsets_host, self.offsets_dev = offsets_host, offsets_dev
-        self.nbr, self._nbr_rev = nbr, None
+        self.nbr, self._nbr_rev, self._mask_rev = nbr, None, None
         self.n_feature, self.n_output, self.kernel_volume = n_feature, n_output, kernel_volume
+        self.mask = _tile_mask(nbr, n_output, kernel_volume)
         self.total_pairs = int(offsets_host[-1]) if offsets_host.numel() else 0
 
     def nbr_rev(self) -> torch.Tensor:
@@ -275,7 +287,12 @@ class _MapCore:
                     )
                 )
             self._nbr_rev = rev
+            self._mask_rev = _tile_mask(rev, self.n_feature, self.kernel_volume)
         return self._nbr_rev
+
+    def mask_rev(self) -> "torch.Tensor | None":
+        self.nbr_rev()
+        return self._mask_rev
 
 
 class GatherScatterDefaultTopology:
@@ -302,6 +319,12 @@ class GatherScatterDefaultTopology:
 
     def _in_map(self) -> torch.Tensor:  # [K^3, pitch]: for each feature row and tap, the output row
         return self._core.nbr if self._reversed else self._core.nbr_rev()
+
+    def _out_mask(self) -> "torch.Tensor | None":
+        return self._core.mask_rev() if self._reversed else self._core.mask
+
+    def _in_mask(self) -> "torch.Tensor | None":
+        return self._core.mask if self._reversed else self._core.mask_rev()
 
     @property
     def device(self) -> torch.device:
@@ -403,7 +426,8 @@ def _pack_weights(weights: torch.Tensor, working: torch.dtype, layout: int) -> t
     return out
 
 
-def _run_conv(x: torch.Tensor, w_packed: torch.Tensor, nbr: torch.Tensor, n_in: int, n_out: int, cin: int, cout: int, k3: int, bias: "torch.Tensor | None" = None) -> torch.Tensor:
+def _run_conv(x: torch.Tensor, w_packed: torch.Tensor, nbr: torch.Tensor, n_in: int, n_out: int, cin: int, cout: int, k3: int,
+              bias: "torch.Tensor | None" = None, tile_mask: "torch.Tensor | None" = None) -> torch.Tensor:
     device, dtype = x.device, x.dtype
     y = torch.empty((n_out, cout), dtype=dtype, device=device)
     if n_out == 0:
@@ -413,7 +437,7 @@ def _run_conv(x: torch.Tensor, w_packed: torch.Tensor, nbr: torch.Tensor, n_in: 
     scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
     check(
         lib.fvc_conv_forward(
-            _ptr(x), _ptr(w_packed), _ptr(bias), y.data_ptr(), _ptr(nbr), int(nbr.shape[1]), n_in, n_out, cin, cout, k3, code, _path,
+            _ptr(x), _ptr(w_packed), _ptr(bias), y.data_ptr(), _ptr(nbr), int(nbr.shape[1]), _ptr(tile_mask), n_in, n_out, cin, cout, k3, code, _path,
             _ptr(scratch), scratch_bytes, _stream(device),
         )
     )
@@ -432,7 +456,7 @@ def _forward(features, weights, topo, name, want_transposed, bias=None):
         w = _pack_weights(weights, working, layout=0)
         if bias is not None:
             bias = bias.to(device=features.device, dtype=working).contiguous()
-        return _run_conv(features, w, topo._out_map(), topo.feature_total_voxels, topo.output_total_voxels, cin, cout, topo.kernel_volume, bias)
+        return _run_conv(features, w, topo._out_map(), topo.feature_total_voxels, topo.output_total_voxels, cin, cout, topo.kernel_volume, bias, topo._out_mask())
 
 
 def _backward(grad_output, features, weights, topo, name, want_transposed):
@@ -460,7 +484,7 @@ def _backward(grad_output, features, weights, topo, name, want_transposed):
         if n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
             grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
         else:
-            grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3)
+            grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3, None, topo._in_mask())
         # wgrad: dW[k] = X[g]^T . dY[s]  (:806-813)
         grad_weights = torch.empty(tuple(weights.shape), dtype=working, device=device)
         scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_out, topo.total_pairs, cin, cout, k3, code))
@@ -471,7 +495,7 @@ def _backward(grad_output, features, weights, topo, name, want_transposed):
             lib.fvc_conv_wgrad(
                 _ptr(features), _ptr(grad_output), _ptr(topo.gather_indices), _ptr(topo.scatter_indices),
                 C.cast(offsets_host.data_ptr(), C.POINTER(C.c_int64)), topo._core.offsets_dev.data_ptr(), _ptr(out_map), int(out_map.shape[1]),
-                n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
+                _ptr(topo._out_mask()), n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
             )
         )
     return grad_features, grad_weights

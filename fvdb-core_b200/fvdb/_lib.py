@@ -53,14 +53,15 @@ SIGNATURES = {
     "fvc_kmap_csr_scratch_bytes": (_sz, [_i64, _i64]),
     "fvc_kmap_to_csr": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fvc_kmap_reverse_dense": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "fvc_kmap_tile_mask": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "fvc_kmap_degree": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "fvc_neighbor_indexes": (C.c_int, [_GB, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "fvc_ijk_to_index": (C.c_int, [_GB, _vp, _vp, _i64, _i32, _vp, _vp]),
     "fvc_pack_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fvc_conv_scratch_bytes": (_sz, [_i64, _i32, _i32, _i64, _i32]),
-    "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
+    "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
     "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64, _i32]),
-    "fvc_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fvc_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
 }
 
 

@@ -159,6 +159,11 @@ FVC_API int fvc_kmap_to_csr(const int32_t *nbr, int64_t pitch, int64_t n_out, in
 FVC_API int fvc_kmap_reverse_dense(const int32_t *gather, const int32_t *scatter, const int64_t *offsets_dev,
                            int64_t kernel_volume, int64_t total_pairs, int64_t n_feature, int32_t *nbr_rev,
                            int64_t pitch_rev, fvc_stream_t stream);
+/* Per 128-row tile of a dense map, a bitmask over taps: bit k of mask[tile * words + (k >> 6)] (words =
+ * ceil(K^3 / 64), bit index k & 63) is set iff some row of the tile has a neighbour through tap k.  The
+ * tensor-core executors use it to skip whole (tile, tap) units: on planar surfaces two thirds of them are empty. */
+FVC_API int fvc_kmap_tile_mask(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, uint64_t *mask,
+                               fvc_stream_t stream);
 /* Per-row degree (number of taps that hit) of a dense map: degree int32 [n_out]. */
 FVC_API int fvc_kmap_degree(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, int32_t *degree,
                     fvc_stream_t stream);
@@ -194,10 +199,11 @@ FVC_API int fvc_pack_weights(const void *weights, const int64_t strides[5], int3
  * no neighbour become 0; GatherScatterDefault.cu:696).  bias (may be NULL): [Cout] in `dtype`, added in
  * the epilogue (fvdb/nn/modules.py:370-371).  path: 0 = automatic (tensor-core kernel when dtype is
  * f16/bf16 and the channel counts allow it, else the CUDA-core kernel), 1 = force CUDA-core path,
- * 2 = force tensor-core path (FVC_ERR_UNSUPPORTED if not admissible). */
+ * 2 = force tensor-core path (FVC_ERR_UNSUPPORTED if not admissible).  tile_mask: fvc_kmap_tile_mask of `nbr`
+ * (may be NULL: no unit skipping). */
 FVC_API size_t fvc_conv_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype);
 FVC_API int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
-                     int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                     const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                      int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
 /* Weight gradient: grad_w[co][ci][k0][k1][k2] = sum over pairs p of tap k of x[gather[p]][ci] * dy[scatter[p]][co]
  * (GatherScatterDefault.cu:806-813), written contiguous in the public layout in `dtype`;
@@ -208,7 +214,7 @@ FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_out, int64_t total_pairs, 
                                     int64_t kernel_volume, int32_t dtype);
 FVC_API int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const int32_t *scatter,
                    const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
-                   int64_t n_in, int64_t n_out,
+                   const uint64_t *tile_mask, int64_t n_in, int64_t n_out,
                    int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, void *grad_w,
                    void *scratch, size_t scratch_bytes, fvc_stream_t stream);
 
