@@ -13,8 +13,10 @@
 //   Stages are recycled by tcgen05.commit -> mbarrier.  Epilogue: tcgen05.ld -> (+bias) -> bf16/f16 -> one
 //   plain 128-bit store stream per output row.
 //
-// Warp roles (192 threads): warps 0-3 gather producers, then epilogue (warp w owns TMEM lanes 32w..32w+31);
-// warp 4 TMEM allocator + MMA issuer; warp 5 weight-chunk loader.
+// Warp roles (224 threads): warps 0-3 gather producers, then epilogue (warp w owns TMEM lanes 32w..32w+31);
+// warp 4 TMEM allocator + MMA issuer; warp 5 weight-chunk loader; warp 6 streams the kernel-map entries of
+// upcoming units into a 16-deep shared-memory ring (one 512-byte cp.async per unit), so the producers never
+// wait on an index load (ncu showed that wait as the top stall of the first version).
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
 
@@ -22,7 +24,8 @@ namespace fvc {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;
+constexpr int TC_IDX_RING = 16;             // map-entry ring depth (units of 128 int32)
 constexpr int TC_TILE_M = 128;
 constexpr int TC_A_BYTES = TC_TILE_M * 128; // one stage: 128 rows x 64 channels x 2 B
 constexpr int TC_MASK_WORDS = 8;            // tile tap-mask words kept in shared memory (K^3 <= 512)
@@ -34,8 +37,8 @@ template <int CIN, int COUT, int TILES, int STAGES> struct TcFwdCfg {
     static constexpr int B_BYTES = COUT * 128;               // one weight chunk: COUT rows x 64 channels x 2 B
     static constexpr int TMEM_COLS = tmem_cols_for(TILES * COUT);
     static constexpr int CTAS_PER_SM = TMEM_COLS <= 256 ? 2 : 1;
-    static constexpr int NUM_BARS = 2 * STAGES + 5;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + 2 * size_t(B_BYTES) + 8 * NUM_BARS + 16;
+    static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * TC_IDX_RING;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + 2 * size_t(B_BYTES) + size_t(TC_IDX_RING) * 512 + 8 * NUM_BARS + 16;
     static_assert(CIN % 64 == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * COUT <= 512, "accumulators exceed TMEM");
 };
@@ -84,11 +87,13 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
-    const uint32_t bars = smem_b + 2 * Cfg::B_BYTES;
+    const uint32_t smem_idx = smem_b + 2 * Cfg::B_BYTES;
+    const uint32_t bars = smem_idx + TC_IDX_RING * 512;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
     const uint32_t bar_accum = bar_bempty + 16;
-    const uint32_t tmem_slot = bar_accum + 8;
+    const uint32_t bar_ifull = bar_accum + 8, bar_iempty = bar_ifull + 8 * TC_IDX_RING;
+    const uint32_t tmem_slot = bar_iempty + 8 * TC_IDX_RING;
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
@@ -117,6 +122,19 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         return (any >> (k & 63)) & 1ull;
     };
 
+    // next active (tap, channel block, tile) unit in [tap][block][tile] order; every role walks the same sequence
+    auto advance = [&](int &k, int &j, int &t) {
+        do {
+            if (++t == ntiles) {
+                t = 0;
+                if (++j == KB) {
+                    j = 0;
+                    ++k;
+                }
+            }
+        } while (k < k3 && !active(k, t));
+    };
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 128); // one arrival per producer thread
@@ -127,6 +145,10 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             mbar_init(bar_bempty + 8 * b, 1);
         }
         mbar_init(bar_accum, 1);
+        for (int e = 0; e < TC_IDX_RING; ++e) {
+            mbar_init(bar_ifull + 8 * e, 32);   // one completion-triggered arrival per index-loader lane
+            mbar_init(bar_iempty + 8 * e, 128); // every producer thread has read its entry
+        }
         fence_mbar_init();
     }
     if (warp == 4)
@@ -138,31 +160,18 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
 
     if (warp < 4) {
         // ================= gather producers =================
-        const int r = threadIdx.x; // this thread fetches the map entry of tile row r
-        auto load_idx = [&](int k, int t) -> int {
-            const int64_t row = (tile0 + t) * TC_TILE_M + r;
-            return row < n_out ? __ldg(nbr + int64_t(k) * pitch + row) : -1;
-        };
-        // walk the active (tap, channel block, tile) units; the map entry of the NEXT active unit is fetched while
-        // the current one is being issued, so the L2 latency of the index load stays off the critical path
-        auto advance = [&](int &k, int &j, int &t) {
-            do {
-                if (++t == ntiles) {
-                    t = 0;
-                    if (++j == KB) {
-                        j = 0;
-                        ++k;
-                    }
-                }
-            } while (k < k3 && !active(k, t));
-        };
+        const int r = threadIdx.x; // this thread reads the map entry of tile row r from the ring
         int k = 0, j = 0, t = -1;
         advance(k, j, t);
-        int idx_next = k < k3 ? load_idx(k, t) : -1;
         for (int u = 0; k < k3; ++u) {
-            const int idx = idx_next, jc = j;
+            const int e = u % TC_IDX_RING;
+            mbar_wait(bar_ifull + 8 * e, (u / TC_IDX_RING) & 1);
+            int idx;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx) : "r"(smem_idx + e * 512 + r * 4) : "memory");
+            if ((tile0 + t) * TC_TILE_M + r >= n_out)
+                idx = -1;
+            const int jc = j;
             advance(k, j, t);
-            idx_next = k < k3 ? load_idx(k, t) : -1;
             const int s = u % STAGES;
             mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
             const uint32_t stage = smem_a + s * TC_A_BYTES;
@@ -174,6 +183,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 const uint16_t *src = x + (src_idx >= 0 ? int64_t(src_idx) * CIN + jc * 64 + q * 8 : 0);
                 cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
             }
+            mbar_arrive(bar_iempty + 8 * e); // ring entry consumed (the shuffles above needed its value)
             // completion-triggered arrival (the CUTLASS sm100 cp.async -> UMMA idiom): the producer never
             // blocks on its own loads, so up to STAGES gathers per CTA stay in flight
             cp_async_arrive_noinc(bar_full + 8 * s);
@@ -253,7 +263,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             umma_commit(bar_accum);
         }
         __syncwarp();
-    } else {
+    } else if (warp == 5) {
         // ================= weight-chunk loader (one thread) =================
         if (lane == 0) {
             int c = 0;
@@ -269,6 +279,18 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             }
         }
         __syncwarp();
+    } else {
+        // ================= kernel-map streamer (whole warp): 128 map entries = 32 lanes x 16 B per unit =================
+        int k = 0, j = 0, t = -1;
+        advance(k, j, t);
+        for (int u = 0; k < k3; ++u) {
+            const int e = u % TC_IDX_RING;
+            mbar_wait(bar_iempty + 8 * e, ((u / TC_IDX_RING) & 1) ^ 1);
+            cp_async16(smem_idx + e * 512 + lane * 16, nbr + int64_t(k) * pitch + (tile0 + t) * TC_TILE_M + lane * 4, 16u);
+            cp_async_arrive_noinc(bar_ifull + 8 * e);
+            advance(k, j, t);
+        }
+        cp_async_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -316,8 +338,10 @@ int tc_forward(const ConvArgs &a) {
     FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core conv scratch too small: %zu < %zu",
                 a.scratch_bytes, need);
     FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0,
-                FVC_ERR_RUNTIME, "tensor-core conv needs 16-byte aligned feature / output / scratch pointers");
+                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.nbr) & 15) == 0,
+                FVC_ERR_RUNTIME, "tensor-core conv needs 16-byte aligned feature / output / scratch / map pointers");
+    FVC_REQUIRE(a.pitch % 4 == 0 && a.pitch >= ceil_div(a.n_out, TC_TILE_M) * TC_TILE_M, FVC_ERR_RUNTIME,
+                "tensor-core conv needs the map pitch (%lld) to be a multiple of 4 covering whole 128-row tiles", (long long)a.pitch);
     uint8_t *img = reinterpret_cast<uint8_t *>(a.scratch);
     const int64_t chunks16 = int64_t(a.k3) * a.cin * a.cout / 8;
     tc_pack_b_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(

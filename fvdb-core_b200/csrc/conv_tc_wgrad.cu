@@ -19,7 +19,8 @@ namespace fvc {
 
 using namespace tc;
 
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 224;
+constexpr int WG_IDX_RING = 8; // ring of kernel-map entries: two taps x 128 int32 per unit
 constexpr int WG_TILE = 128;
 constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 channels x 2 B
 
@@ -29,8 +30,8 @@ template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
     static constexpr int MAX_UNITS = 512 / COUT;   // accumulators that fit TMEM
     static constexpr int A_STAGE = 2 * WG_BLOCK_BYTES;
     static constexpr int B_STAGE = NB * WG_BLOCK_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 5;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + 2 * size_t(B_STAGE) + 8 * NUM_BARS + 16;
+    static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * WG_IDX_RING;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + 2 * size_t(B_STAGE) + size_t(WG_IDX_RING) * 1024 + 8 * NUM_BARS + 16;
     static_assert(CIN % 64 == 0 && COUT % 64 == 0 && CIN <= 256 && COUT <= 256, "unsupported channel counts");
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -59,11 +60,13 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * Cfg::A_STAGE;
-    const uint32_t bars = smem_b + 2 * Cfg::B_STAGE;
+    const uint32_t smem_idx = smem_b + 2 * Cfg::B_STAGE;
+    const uint32_t bars = smem_idx + WG_IDX_RING * 1024;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
     const uint32_t bar_accum = bar_bempty + 16;
-    const uint32_t tmem_slot = bar_accum + 8;
+    const uint32_t bar_ifull = bar_accum + 8, bar_iempty = bar_ifull + 8 * WG_IDX_RING;
+    const uint32_t tmem_slot = bar_iempty + 8 * WG_IDX_RING;
     __shared__ uint32_t s_started; // units whose accumulator was written at least once (MMA thread -> epilogue)
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + (tmem_slot - smem_base));
@@ -105,6 +108,10 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             mbar_init(bar_bempty + 8 * b, 1);
         }
         mbar_init(bar_accum, 1);
+        for (int e = 0; e < WG_IDX_RING; ++e) {
+            mbar_init(bar_ifull + 8 * e, 32);
+            mbar_init(bar_iempty + 8 * e, 128);
+        }
         fence_mbar_init();
     }
     if (warp == 4)
@@ -117,9 +124,6 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     if (warp < 4) {
         // ================= producers: dY tile, then the gathered X blocks of every unit =================
         const int r = threadIdx.x;
-        auto tap_idx = [&](int block, int64_t row) -> int { // map entry for A block `block` (tap = block / CB)
-            return (block < total_blocks && row < n_out) ? __ldg(nbr + int64_t(block / CB) * pitch + row) : -1;
-        };
         int u = 0, tb = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
             const int64_t row = tile * WG_TILE + r;
@@ -133,31 +137,27 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     gather_block(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES, dy, COUT, nb * 64, self, warp, lane);
                 cp_async_arrive_noinc(bar_bfull + 8 * bs);
             }
-            // live units of this tile; the NEXT live unit's map entries are fetched while the current one is issued
-            int ul = 0;
-            while (ul < nunits && !unit_live(m0, m1, ul))
-                ++ul;
-            int idx0 = -1, idx1 = -1;
-            if (ul < nunits) {
-                idx0 = tap_idx(2 * (unit0 + ul), row);
-                idx1 = tap_idx(2 * (unit0 + ul) + 1, row);
-            }
-            for (; ul < nunits; ++u) {
+            for (int ul = 0; ul < nunits; ++ul) {
+                if (!unit_live(m0, m1, ul))
+                    continue;
                 const int blk = 2 * (unit0 + ul);
-                const int cur0 = idx0, cur1 = idx1;
-                do {
-                    ++ul;
-                } while (ul < nunits && !unit_live(m0, m1, ul));
-                if (ul < nunits) {
-                    idx0 = tap_idx(2 * (unit0 + ul), row);
-                    idx1 = tap_idx(2 * (unit0 + ul) + 1, row);
-                }
+                const int e = u % WG_IDX_RING;
+                mbar_wait(bar_ifull + 8 * e, (u / WG_IDX_RING) & 1);
+                int idx0, idx1;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx0) : "r"(smem_idx + e * 1024 + r * 4) : "memory");
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1) : "r"(smem_idx + e * 1024 + 512 + r * 4) : "memory");
+                if (row >= n_out)
+                    idx0 = idx1 = -1;
+                if (blk + 1 >= total_blocks)
+                    idx1 = -1; // odd block count: the last unit's second block is a zero dummy
                 const int s = u % STAGES;
                 mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
                 const uint32_t stage = smem_a + s * Cfg::A_STAGE;
-                gather_block(stage, x, CIN, (blk % CB) * 64, cur0, warp, lane);
-                gather_block(stage + WG_BLOCK_BYTES, x, CIN, ((blk + 1) % CB) * 64, cur1, warp, lane);
+                gather_block(stage, x, CIN, (blk % CB) * 64, idx0, warp, lane);
+                gather_block(stage + WG_BLOCK_BYTES, x, CIN, ((blk + 1) % CB) * 64, idx1, warp, lane);
+                mbar_arrive(bar_iempty + 8 * e);
                 cp_async_arrive_noinc(bar_full + 8 * s);
+                ++u;
             }
         }
         cp_async_wait_all();
@@ -226,6 +226,25 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             umma_commit(bar_accum);
         }
         __syncwarp();
+    } else if (warp == 6) {
+        // ================= kernel-map streamer (whole warp): both taps of every live unit, 2 x 512 B =================
+        int u = 0;
+        for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+            const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
+            for (int ul = 0; ul < nunits; ++ul) {
+                if (!unit_live(m0, m1, ul))
+                    continue;
+                const int blk = 2 * (unit0 + ul);
+                const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
+                const int e = u % WG_IDX_RING;
+                mbar_wait(bar_iempty + 8 * e, ((u / WG_IDX_RING) & 1) ^ 1);
+                cp_async16(smem_idx + e * 1024 + lane * 16, nbr + int64_t(ta) * pitch + tile * WG_TILE + lane * 4, 16u);
+                cp_async16(smem_idx + e * 1024 + 512 + lane * 16, nbr + int64_t(tb_) * pitch + tile * WG_TILE + lane * 4, 16u);
+                cp_async_arrive_noinc(bar_ifull + 8 * e);
+                ++u;
+            }
+        }
+        cp_async_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -293,20 +312,22 @@ int tc_wgrad(const WgradArgs &a) {
     FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core wgrad scratch too small: %zu < %zu",
                 a.scratch_bytes, need);
     FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0,
+                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.nbr) & 15) == 0,
                 FVC_ERR_RUNTIME, "tensor-core wgrad needs 16-byte aligned pointers");
+    FVC_REQUIRE(a.pitch % 4 == 0 && a.pitch >= ceil_div(a.n_out, WG_TILE) * WG_TILE, FVC_ERR_RUNTIME,
+                "tensor-core wgrad needs the map pitch (%lld) to be a multiple of 4 covering whole 128-row tiles", (long long)a.pitch);
 #define FVC_WG_CASE(CI, CO, S)       \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S>(a);
     FVC_WG_CASE(64, 64, 4)
     FVC_WG_CASE(64, 128, 4)
-    FVC_WG_CASE(64, 256, 3)
+    FVC_WG_CASE(64, 256, 2)
     FVC_WG_CASE(128, 64, 4)
     FVC_WG_CASE(128, 128, 4)
-    FVC_WG_CASE(128, 256, 3)
+    FVC_WG_CASE(128, 256, 2)
     FVC_WG_CASE(256, 64, 4)
     FVC_WG_CASE(256, 128, 4)
-    FVC_WG_CASE(256, 256, 3)
+    FVC_WG_CASE(256, 256, 2)
 #undef FVC_WG_CASE
     return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core wgrad kernel for channels %d -> %d", a.cin, a.cout);
 }

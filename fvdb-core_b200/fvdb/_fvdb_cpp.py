@@ -247,6 +247,11 @@ def ijk_to_index(grid: GridBatchData, ijk: torch.Tensor, jidx: "torch.Tensor | N
 # ---------------------------------------------------------------------------------------------
 
 
+def _map_pitch(rows: int) -> int:
+    """Row pitch of a tap-major dense map: whole 128-row tiles, so the executors can stream 16-byte map chunks."""
+    return max((rows + 127) // 128 * 128, 128)
+
+
 def _tile_mask(nbr: torch.Tensor, rows: int, kernel_volume: int) -> "torch.Tensor | None":
     """Per 128-row tile tap bitmask of a dense map (fvc_kmap_tile_mask); lets the executors skip empty units."""
     if rows == 0 or kernel_volume == 0 or kernel_volume > 4096:
@@ -277,7 +282,7 @@ class _MapCore:
     def nbr_rev(self) -> torch.Tensor:
         if self._nbr_rev is None:
             device = self.nbr.device
-            pitch = max(self.n_feature, 1)
+            pitch = _map_pitch(self.n_feature)
             rev = torch.empty((self.kernel_volume, pitch), dtype=torch.int32, device=device)
             with torch.cuda.device(device):
                 check(
@@ -339,7 +344,7 @@ def _build_topology(feature_grid: GridBatchData, output_grid: GridBatchData, ker
     _require_cuda(device, "gs_build_topology")
     k3 = ks[0] * ks[1] * ks[2]
     n_out, n_feat = output_grid.total_voxels, feature_grid.total_voxels
-    pitch = max(n_out, 1)
+    pitch = _map_pitch(n_out)
     with torch.cuda.device(device):
         stream = _stream(device)
         nbr = torch.empty((k3, pitch), dtype=torch.int32, device=device)
