@@ -1,0 +1,170 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, host-only geometry entry
+points, JaggedTensor, plan policy helpers, grid partitioning and the world_size-2 gloo gradient all-reduce."""
+
+import os
+import re
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_abi_exports_every_declared_symbol():
+    import ctypes
+
+    from fvdb import _lib
+
+    header = (REPO / "include" / "fvdbconv.h").read_text()
+    declared = set(re.findall(r"FVC_API\s+[\w\s\*]+?\b(fvc_\w+)\s*\(", header))
+    assert len(declared) >= 25
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(str(REPO / "fvdb-core_b200" / "fvdb" / "libfvdbconv.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"libfvdbconv.so does not export {name}"
+    assert _lib.lib.fvc_abi_version() == 1
+
+
+def test_geometry_entry_points_match_oracle_and_reference_kats():
+    import fvdb
+    import oracle
+
+    g = fvdb._fvdb_cpp.ConvolutionGeometry([4, 3, 6], [2, 3, 4])
+    assert (g.kernel_volume, g.padding_before, g.padding_after) == (72, [1, 1, 2], [2, 1, 3])
+    assert g.tap_coord(23) == [1, 0, 5] and g.fine_from_coarse([3, -2, 1], [0, 0, 0]) == [5, -7, 2]
+    assert g.semantics_version == 1 and g.phase_policy == "torch_same_phase" and g.dilation == [1, 1, 1] and g.registration_offset == [0, 0, 0]
+    g4 = fvdb._fvdb_cpp.ConvolutionGeometry([4, 4, 4], [4, 4, 4])
+    assert g4.coarse_from_fine([-2, -2, -2], [3, 3, 3]) == [-1, -1, -1] and g4.coarse_from_fine([-2, -2, -2], [2, 2, 2]) is None
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        ks, st = rng.integers(1, 7, 3).tolist(), rng.integers(1, 6, 3).tolist()
+        geo, ref = fvdb._fvdb_cpp.ConvolutionGeometry(ks, st), oracle.Geometry(ks, st)
+        tap = ref.tap_coord(int(rng.integers(0, ref.kernel_volume)))
+        c = rng.integers(-50, 50, 3).tolist()
+        assert geo.fine_from_coarse(c, tap) == ref.fine_from_coarse(c, tap).tolist()
+        coarse, ok = ref.coarse_from_fine(c, tap)
+        assert geo.coarse_from_fine(c, tap) == (coarse.tolist() if bool(ok) else None)
+    with pytest.raises(ValueError, match="kernel_size must be strictly positive"):
+        fvdb._fvdb_cpp.ConvolutionGeometry([0, 1, 1], [1, 1, 1])
+    with pytest.raises(ValueError, match="stride must be strictly positive"):
+        fvdb._fvdb_cpp.ConvolutionGeometry([1, 1, 1], [1, -2, 1])
+    with pytest.raises(IndexError):
+        g.tap_coord(72)
+
+
+def test_no_cpu_fallback():
+    import fvdb
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(torch.zeros((4, 3), dtype=torch.int32)))
+
+
+def test_jagged_tensor_subset():
+    from fvdb import JaggedTensor
+
+    a, b = torch.arange(6.0).reshape(3, 2), torch.arange(4.0).reshape(2, 2) + 10
+    jt = JaggedTensor([a, b])
+    assert jt.num_tensors == 2 and jt.joffsets.tolist() == [0, 3, 5] and jt.jidx.tolist() == [0, 0, 0, 1, 1] and jt.jidx.dtype == torch.int32
+    assert torch.equal(jt[1].jdata, b) and [t.shape[0] for t in jt.unbind()] == [3, 2] and jt.lshape == [3, 2]
+    like = jt.jagged_like(torch.zeros(5, 7))
+    assert like.rshape == (5, 7) and like.joffsets.tolist() == [0, 3, 5]
+    with pytest.raises(ValueError):
+        jt.jagged_like(torch.zeros(4, 7))
+    jt.jdata = jt.jdata + 1
+    assert float(jt.jdata[0, 0]) == 1.0
+    assert torch.equal((jt * 2).jdata, jt.jdata * 2)
+    single = JaggedTensor(a)
+    assert single.num_tensors == 1 and single.joffsets.tolist() == [0, 3]
+    off = JaggedTensor.from_data_and_offsets(torch.zeros(5, 1), torch.tensor([0, 0, 5]))
+    assert off.num_tensors == 2 and off.jidx.tolist() == [1] * 5
+    with pytest.raises(ValueError):
+        JaggedTensor([a, torch.zeros(2, 3)])
+
+
+def test_plan_policy_helpers_and_types():
+    import fvdb
+    from fvdb import convolution_plan as cp
+    from fvdb.types import ValueConstraint, to_Vec3i
+
+    assert to_Vec3i(3).tolist() == [3, 3, 3] and to_Vec3i([1, 2, 3]).tolist() == [1, 2, 3]
+    with pytest.raises(ValueError):
+        to_Vec3i(0, value_constraint=ValueConstraint.POSITIVE)
+    with pytest.raises(TypeError):
+        to_Vec3i(1.5)
+    P = fvdb.ConvolutionTopologyPolicy
+    assert cp._resolve_topology_policy(None, None) is P.COMPLETE and cp._resolve_topology_policy(object(), None) is P.RESTRICTED
+    with pytest.raises(ValueError, match="COMPLETE.*target_grid=None"):
+        cp._resolve_topology_policy(object(), P.COMPLETE)
+    with pytest.raises(TypeError):
+        cp._resolve_topology_policy(None, "complete")
+    cp._WARNED_INCOMPLETE_COVERAGE_GEOMETRIES.clear()
+    geo = fvdb._fvdb_cpp.ConvolutionGeometry([1, 1, 1], [2, 2, 2])
+    with pytest.warns(fvdb.ConvolutionCoverageWarning, match="uncovered stride residues"):
+        cp._warn_if_incomplete_residue_coverage(geo, False)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        cp._warn_if_incomplete_residue_coverage(geo, False)  # once per geometry
+        cp._warn_if_incomplete_residue_coverage(fvdb._fvdb_cpp.ConvolutionGeometry([3, 3, 3], [2, 2, 2]), False)  # full coverage
+    with pytest.raises(ValueError, match="uniform kernel sizes 3, 5, 7"):
+        cp._validate_pred_gather_igemm_admission(torch.tensor([3, 3, 5]), torch.tensor([1, 1, 1]), (), transposed=False)
+    with pytest.raises(ValueError, match="uniform strides 1, 2"):
+        cp._validate_pred_gather_igemm_admission(torch.tensor([3, 3, 3]), torch.tensor([3, 3, 3]), (), transposed=False)
+    assert cp._matmul_weight_matrix(torch.zeros(4, 2, 1, 1, 1)).shape == (4, 2)
+    m = fvdb.nn.SparseConv3d(4, 8, 3)
+    assert m.weight.shape == (8, 4, 3, 3, 3) and m.weight.stride() == (1, 8, 32, 96, 288) and m.bias.shape == (8,)
+    assert fvdb.nn.SparseConv3d(4, 8, 1).weight.shape == (8, 4)
+    bound = 1 / (4 * 27) ** 0.5
+    assert float(m.weight.abs().max()) <= bound and set(m.state_dict()) == {"weight", "bias"}
+
+
+def test_partition_grids_lpt():
+    from fvdb.distributed import partition_grids_lpt
+
+    counts = [1000, 10, 900, 20, 500, 480, 30, 5]
+    for world in (1, 2, 3, 8):
+        bins = partition_grids_lpt(counts, world)
+        assert sorted(g for b in bins for g in b) == list(range(8)) and len(bins) == world
+    two = partition_grids_lpt(counts, 2)
+    loads = [sum(counts[g] for g in b) for b in two]
+    assert abs(loads[0] - loads[1]) <= 100
+    assert partition_grids_lpt([5, 5], 4) == [[0], [1], [], []]
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _allreduce_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, str(REPO / "fvdb-core_b200"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fvdb.distributed import allreduce_gradients, partition_grids_lpt
+
+    torch.manual_seed(0)
+    weights = [torch.nn.Parameter(torch.zeros(8, 4, 3, 3, 3)), torch.nn.Parameter(torch.zeros(8)), torch.nn.Parameter(torch.zeros(3, dtype=torch.float64))]
+    mine = partition_grids_lpt([7, 3, 5, 1], world)[rank]  # each rank owns whole grids
+    for p in weights:  # a rank's "wgrad" = sum over its own grids of a per-grid contribution
+        p.grad = sum((torch.full_like(p, float(g + 1)) for g in mine), torch.zeros_like(p))
+    calls = allreduce_gradients(weights, bucket_bytes=1 << 12)
+    assert calls >= 2
+    for p in weights:
+        assert torch.equal(p.grad, torch.full_like(p, float(1 + 2 + 3 + 4)))  # identical to the single-process sum
+    dist.barrier()
+    dist.destroy_process_group()
+    Path(out_dir, f"ok{rank}").write_text("ok")
+
+
+def test_wgrad_allreduce_world_size_2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
