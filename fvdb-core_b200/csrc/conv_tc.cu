@@ -13,18 +13,24 @@
 //   Stages are recycled by tcgen05.commit -> mbarrier.  Epilogue: tcgen05.ld -> (+bias) -> bf16/f16 -> one
 //   plain 128-bit store stream per output row.
 //
-// Warp roles (224 threads): warps 0-3 gather producers, then epilogue (warp w owns TMEM lanes 32w..32w+31);
-// warp 4 TMEM allocator + MMA issuer; warp 5 weight-chunk loader; warp 6 streams the kernel-map entries of
-// upcoming units into a 16-deep shared-memory ring (one 512-byte cp.async per unit), so the producers never
-// wait on an index load (ncu showed that wait as the top stall of the first version).
+// Warp roles (352 threads): warps 0-7 gather producers, then epilogue (warp w owns TMEM lanes 32*(w&3)..+31 of the
+// tiles with parity w>>2); warp 8 TMEM allocator + MMA issuer; warp 9 weight-chunk loader; warp 10 streams the
+// kernel-map entries of upcoming units into a 16-deep shared-memory ring (one 512-byte cp.async per unit), so the
+// producers never wait on an index load (ncu showed that wait as the top stall of the first version; the second
+// showed the producers' own instruction stream, hence 8 producer warps and a bit-scan unit iterator).
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
+
+#include <cstdlib>
 
 namespace fvc {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 224;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
+constexpr int TC_WARP_MMA = TC_PRODUCER_WARPS, TC_WARP_B = TC_PRODUCER_WARPS + 1;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 3) * 32;
 constexpr int TC_IDX_RING = 16;             // map-entry ring depth (units of 128 int32)
 constexpr int TC_TILE_M = 128;
 constexpr int TC_A_BYTES = TC_TILE_M * 128; // one stage: 128 rows x 64 channels x 2 B
@@ -32,13 +38,15 @@ constexpr int TC_MASK_WORDS = 8;            // tile tap-mask words kept in share
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-template <int CIN, int COUT, int TILES, int STAGES> struct TcFwdCfg {
+template <int CIN, int COUT, int TILES, int STAGES, int BST> struct TcFwdCfg {
     static constexpr int KB = CIN / 64;                      // 64-channel reduction blocks per tap
     static constexpr int B_BYTES = COUT * 128;               // one weight chunk: COUT rows x 64 channels x 2 B
     static constexpr int TMEM_COLS = tmem_cols_for(TILES * COUT);
-    static constexpr int CTAS_PER_SM = TMEM_COLS <= 256 ? 2 : 1;
-    static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * TC_IDX_RING;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + 2 * size_t(B_BYTES) + size_t(TC_IDX_RING) * 512 + 8 * NUM_BARS + 16;
+    static constexpr int NUM_BARS = 2 * STAGES + 2 * BST + 1 + 2 * TC_IDX_RING;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TC_IDX_RING) * 512 + 8 * NUM_BARS + 16;
+    // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (227 KB per SM, 1 KB reserved per CTA)
+    static constexpr int CTAS_PER_SM = (512 / TMEM_COLS) < int(232448 / (SMEM + 1024)) ? (512 / TMEM_COLS) : int(232448 / (SMEM + 1024));
+    static_assert(CTAS_PER_SM >= 1, "configuration does not fit one SM");
     static_assert(CIN % 64 == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * COUT <= 512, "accumulators exceed TMEM");
 };
@@ -76,22 +84,22 @@ __device__ __forceinline__ float half_to_float(uint16_t v, bool bf16) {
     return bf16 ? __bfloat162float(*reinterpret_cast<__nv_bfloat16 *>(&v)) : __half2float(*reinterpret_cast<__half *>(&v));
 }
 
-template <int CIN, int COUT, int TILES, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, (TcFwdCfg<CIN, COUT, TILES, STAGES>::CTAS_PER_SM))
+template <int CIN, int COUT, int TILES, int STAGES, int BST>
+__global__ void __launch_bounds__(TC_THREADS, (TcFwdCfg<CIN, COUT, TILES, STAGES, BST>::CTAS_PER_SM > 2 ? 2 : TcFwdCfg<CIN, COUT, TILES, STAGES, BST>::CTAS_PER_SM))
 conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_img, const uint16_t *__restrict__ bias,
                    uint16_t *__restrict__ y, const int32_t *__restrict__ nbr, int64_t pitch,
                    const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, uint32_t idesc, int is_bf16) {
-    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES>;
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST>;
     constexpr int KB = Cfg::KB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
-    const uint32_t smem_idx = smem_b + 2 * Cfg::B_BYTES;
+    const uint32_t smem_idx = smem_b + BST * Cfg::B_BYTES;
     const uint32_t bars = smem_idx + TC_IDX_RING * 512;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
-    const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
-    const uint32_t bar_accum = bar_bempty + 16;
+    const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 8 * BST;
+    const uint32_t bar_accum = bar_bempty + 8 * BST;
     const uint32_t bar_ifull = bar_accum + 8, bar_iempty = bar_ifull + 8 * TC_IDX_RING;
     const uint32_t tmem_slot = bar_iempty + 8 * TC_IDX_RING;
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -102,113 +110,115 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const int64_t tile0 = int64_t(blockIdx.x) * TILES;
     const int ntiles = int(total_tiles - tile0 < TILES ? total_tiles - tile0 : TILES);
 
-    // tap bitmask of every tile this CTA owns: (tile, tap) units without a single valid row are skipped by all roles
-    __shared__ unsigned long long s_tmask[TILES][TC_MASK_WORDS];
+    // s_tiles[k]: bit t set iff tile t of this CTA has a row with a neighbour through tap k.  Units whose bit is
+    // clear are skipped by every role (about half of all units on planar scenes).
+    __shared__ uint8_t s_tiles[64 * TC_MASK_WORDS];
     {
         const int words = (k3 + 63) >> 6;
-        for (int i = threadIdx.x; i < TILES * TC_MASK_WORDS; i += TC_THREADS) {
-            const int t = i / TC_MASK_WORDS, w = i % TC_MASK_WORDS;
-            unsigned long long m = 0ull;
-            if (t < ntiles && w < words)
-                m = tile_mask ? __ldg(tile_mask + (tile0 + t) * words + w) : ~0ull;
-            s_tmask[t][w] = m;
+        for (int k = threadIdx.x; k < k3; k += TC_THREADS) {
+            uint32_t bits = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const unsigned long long m = tile_mask ? __ldg(tile_mask + (tile0 + t) * words + (k >> 6)) : ~0ull;
+                bits |= uint32_t((m >> (k & 63)) & 1ull) << t;
+            }
+            s_tiles[k] = uint8_t(bits);
         }
     }
-    auto active = [&](int k, int t) -> bool { return (s_tmask[t][k >> 6] >> (k & 63)) & 1ull; };
-    auto tap_any = [&](int k) -> bool {
-        unsigned long long any = 0ull;
-        for (int t = 0; t < ntiles; ++t)
-            any |= s_tmask[t][k >> 6];
-        return (any >> (k & 63)) & 1ull;
-    };
-
-    // next active (tap, channel block, tile) unit in [tap][block][tile] order; every role walks the same sequence
-    auto advance = [&](int &k, int &j, int &t) {
+    // next active (tap, channel block, tile) unit in [tap][block][tile] order; every role walks the same sequence.
+    // `bits` caches s_tiles[k]; start with k = -1.
+    auto advance = [&](int &k, int &j, int &t, uint32_t &bits) {
+        const uint32_t rest = k >= 0 ? bits & ~((2u << t) - 1u) : 0u;
+        if (rest) {
+            t = __ffs(rest) - 1;
+            return;
+        }
+        if (k >= 0 && ++j < KB) {
+            t = __ffs(bits) - 1;
+            return;
+        }
+        j = 0;
         do {
-            if (++t == ntiles) {
-                t = 0;
-                if (++j == KB) {
-                    j = 0;
-                    ++k;
-                }
-            }
-        } while (k < k3 && !active(k, t));
+            ++k;
+        } while (k < k3 && (bits = s_tiles[k]) == 0u);
+        t = k < k3 ? __ffs(bits) - 1 : 0;
     };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 128); // one arrival per producer thread
-            mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS); // one completion-triggered arrival per producer thread
+            mbar_init(bar_empty + 8 * s, 1);            // tcgen05.commit
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < BST; ++b) {
             mbar_init(bar_bfull + 8 * b, 1); // expect_tx arrival + bytes
             mbar_init(bar_bempty + 8 * b, 1);
         }
         mbar_init(bar_accum, 1);
         for (int e = 0; e < TC_IDX_RING; ++e) {
-            mbar_init(bar_ifull + 8 * e, 32);   // one completion-triggered arrival per index-loader lane
-            mbar_init(bar_iempty + 8 * e, 128); // every producer thread has read its entry
+            mbar_init(bar_ifull + 8 * e, 32);            // one completion-triggered arrival per streamer lane
+            mbar_init(bar_iempty + 8 * e, TC_PRODUCERS); // every producer thread has read its entries
         }
         fence_mbar_init();
     }
-    if (warp == 4)
+    if (warp == TC_WARP_MMA)
         tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 4) {
-        // ================= gather producers =================
-        const int r = threadIdx.x; // this thread reads the map entry of tile row r from the ring
-        int k = 0, j = 0, t = -1;
-        advance(k, j, t);
+    if (warp < TC_PRODUCER_WARPS) {
+        // ================= gather producers: warp w copies rows [16w, 16w+16) of the tile, 4 rows per instruction ====
+        const int q = lane & 7, rsub = lane >> 3;
+        int k = -1, j = 0, t = 0;
+        uint32_t bits = 0;
+        advance(k, j, t, bits);
         for (int u = 0; k < k3; ++u) {
             const int e = u % TC_IDX_RING;
             mbar_wait(bar_ifull + 8 * e, (u / TC_IDX_RING) & 1);
-            int idx;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx) : "r"(smem_idx + e * 512 + r * 4) : "memory");
-            if ((tile0 + t) * TC_TILE_M + r >= n_out)
-                idx = -1;
-            const int jc = j;
-            advance(k, j, t);
+            int idx[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx[i]) : "r"(smem_idx + e * 512 + (warp * 16 + 4 * i + rsub) * 4) : "memory");
+            const int64_t row0 = (tile0 + t) * TC_TILE_M + warp * 16 + rsub;
+            const int col = j * 64 + q * 8;
+            advance(k, j, t, bits);
             const int s = u % STAGES;
             mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
             const uint32_t stage = smem_a + s * TC_A_BYTES;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { // 8 lanes cover one 128-byte row; 4 rows per warp instruction
-                const int rl = 4 * i + (lane >> 3);
-                const int row = warp * 32 + rl, q = lane & 7;
-                const int src_idx = __shfl_sync(0xffffffffu, idx, rl);
-                const uint16_t *src = x + (src_idx >= 0 ? int64_t(src_idx) * CIN + jc * 64 + q * 8 : 0);
-                cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
+            for (int i = 0; i < 4; ++i) { // 8 lanes cover one 128-byte row (one full line)
+                const int row = warp * 16 + 4 * i + rsub;
+                const bool ok = idx[i] >= 0 && row0 + 4 * i < n_out;
+                const uint16_t *src = x + (ok ? int64_t(idx[i]) * CIN + col : 0);
+                cp_async16(stage + row * 128 + ((q ^ (row & 7)) << 4), src, ok ? 16u : 0u);
             }
-            mbar_arrive(bar_iempty + 8 * e); // ring entry consumed (the shuffles above needed its value)
-            // completion-triggered arrival (the CUTLASS sm100 cp.async -> UMMA idiom): the producer never
-            // blocks on its own loads, so up to STAGES gathers per CTA stay in flight
+            mbar_arrive(bar_iempty + 8 * e); // ring entry consumed (its values are in registers)
+            // completion-triggered arrival (the CUTLASS sm100 cp.async -> UMMA idiom): the producer never blocks on
+            // its own loads, so up to STAGES gathers per CTA stay in flight
             cp_async_arrive_noinc(bar_full + 8 * s);
         }
         cp_async_wait_all();
 
-        // ================= epilogue =================
+        // ================= epilogue: warp w drains TMEM lanes 32*(w&3).., tiles of parity w>>2 =================
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         const bool bf16 = is_bf16 != 0;
-        for (int t = 0; t < ntiles; ++t) {
-            const int64_t row = (tile0 + t) * TC_TILE_M + warp * 32 + lane;
-            unsigned long long live = 0ull; // a tile no tap reaches was never accumulated: its rows are zero
-            for (int w = 0; w < TC_MASK_WORDS; ++w)
-                live |= s_tmask[t][w];
+        const int quarter = warp & 3;
+        for (int tt = warp >> 2; tt < ntiles; tt += TC_PRODUCER_WARPS / 4) {
+            const int64_t row = (tile0 + tt) * TC_TILE_M + quarter * 32 + lane;
+            bool live = false; // a tile no tap reaches was never accumulated: its rows are zero
+            for (int kk = 0; kk < k3; ++kk)
+                live = live || ((s_tiles[kk] >> tt) & 1u);
 #pragma unroll
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t acc[32];
                 if (live) {
-                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(t * COUT + c0), acc);
+                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(tt * COUT + c0), acc);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        acc[e] = 0u;
+                    for (int z = 0; z < 32; ++z)
+                        acc[z] = 0u;
                 }
                 if (row < n_out) {
                     uint4 *dst = reinterpret_cast<uint4 *>(y + row * COUT + c0);
@@ -229,21 +239,21 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TC_WARP_MMA) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             int u = 0, c = 0;
             uint32_t started = 0; // tiles whose accumulator has been written at least once
             for (int k = 0; k < k3; ++k) {
-                if (!tap_any(k))
+                const uint32_t tiles = s_tiles[k];
+                if (!tiles)
                     continue;
                 for (int j = 0; j < KB; ++j, ++c) {
-                    const int b = c & 1;
-                    mbar_wait(bar_bfull + 8 * b, (c >> 1) & 1);
+                    const int b = c % BST;
+                    mbar_wait(bar_bfull + 8 * b, (c / BST) & 1);
                     const uint32_t b_base = smem_b + b * Cfg::B_BYTES;
-                    for (int t = 0; t < ntiles; ++t) {
-                        if (!active(k, t))
-                            continue;
+                    for (uint32_t rest = tiles; rest; rest &= rest - 1u, ++u) {
+                        const int t = __ffs(rest) - 1;
                         const int s = u % STAGES;
                         mbar_wait(bar_full + 8 * s, (u / STAGES) & 1);
                         tc_fence_after();
@@ -255,7 +265,6 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                                      make_smem_desc_sw128(b_base + kk * 32, 16, 1024), idesc, (acc0 | uint32_t(kk != 0)));
                         umma_commit(bar_empty + 8 * s); // stage reusable once these MMAs retire
                         started |= 1u << t;
-                        ++u;
                     }
                     umma_commit(bar_bempty + 8 * b);
                 }
@@ -263,16 +272,16 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             umma_commit(bar_accum);
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == TC_WARP_B) {
         // ================= weight-chunk loader (one thread) =================
         if (lane == 0) {
             int c = 0;
             for (int k = 0; k < k3; ++k) {
-                if (!tap_any(k))
+                if (!s_tiles[k])
                     continue;
                 for (int j = 0; j < KB; ++j, ++c) {
-                    const int b = c & 1;
-                    mbar_wait(bar_bempty + 8 * b, ((c >> 1) & 1) ^ 1);
+                    const int b = c % BST;
+                    mbar_wait(bar_bempty + 8 * b, ((c / BST) & 1) ^ 1);
                     mbar_expect_tx(bar_bfull + 8 * b, Cfg::B_BYTES);
                     bulk_g2s(smem_b + b * Cfg::B_BYTES, w_img + int64_t(k * KB + j) * Cfg::B_BYTES, Cfg::B_BYTES, bar_bfull + 8 * b);
                 }
@@ -281,27 +290,28 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         __syncwarp();
     } else {
         // ================= kernel-map streamer (whole warp): 128 map entries = 32 lanes x 16 B per unit =================
-        int k = 0, j = 0, t = -1;
-        advance(k, j, t);
+        int k = -1, j = 0, t = 0;
+        uint32_t bits = 0;
+        advance(k, j, t, bits);
         for (int u = 0; k < k3; ++u) {
             const int e = u % TC_IDX_RING;
             mbar_wait(bar_iempty + 8 * e, ((u / TC_IDX_RING) & 1) ^ 1);
             cp_async16(smem_idx + e * 512 + lane * 16, nbr + int64_t(k) * pitch + (tile0 + t) * TC_TILE_M + lane * 4, 16u);
             cp_async_arrive_noinc(bar_ifull + 8 * e);
-            advance(k, j, t);
+            advance(k, j, t, bits);
         }
         cp_async_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4)
+    if (warp == TC_WARP_MMA)
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-template <int CIN, int COUT, int TILES, int STAGES> static int launch_tc_fwd(const ConvArgs &a, const uint8_t *w_img) {
-    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES>;
-    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES>;
+template <int CIN, int COUT, int TILES, int STAGES, int BST> static int launch_tc_fwd(const ConvArgs &a, const uint8_t *w_img) {
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST>;
+    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES, BST>;
     static bool configured = false; // per instantiation
     if (!configured) {
         FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
@@ -347,21 +357,35 @@ int tc_forward(const ConvArgs &a) {
     tc_pack_b_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
         reinterpret_cast<const uint16_t *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
     FVC_LAUNCH_CHECK();
-#define FVC_TC_CASE(CI, CO, T, S)    \
+    // experiment knob (scripts/bench_variants.py): alternative pipeline shapes for the 64 -> 64 kernel
+    if (a.cin == 64 && a.cout == 64) {
+        const char *v = getenv("FVC_TC_VARIANT");
+        const int variant = v ? atoi(v) : 0;
+        switch (variant) {
+        case 1: return launch_tc_fwd<64, 64, 4, 4, 4>(a, img);
+        case 2: return launch_tc_fwd<64, 64, 8, 9, 4>(a, img);
+        case 3: return launch_tc_fwd<64, 64, 4, 3, 2>(a, img);
+        case 4: return launch_tc_fwd<64, 64, 2, 4, 4>(a, img);
+        case 5: return launch_tc_fwd<64, 64, 4, 5, 2>(a, img);
+        case 6: return launch_tc_fwd<64, 64, 8, 6, 6>(a, img);
+        default: break;
+        }
+    }
+#define FVC_TC_CASE(CI, CO, T, S, B) \
     if (a.cin == CI && a.cout == CO) \
-        return launch_tc_fwd<CI, CO, T, S>(a, img);
-    FVC_TC_CASE(64, 32, 8, 5)
-    FVC_TC_CASE(64, 64, 4, 5)
-    FVC_TC_CASE(64, 128, 4, 8)
-    FVC_TC_CASE(64, 256, 2, 8)
-    FVC_TC_CASE(128, 32, 8, 5)
-    FVC_TC_CASE(128, 64, 4, 5)
-    FVC_TC_CASE(128, 128, 4, 8)
-    FVC_TC_CASE(128, 256, 2, 8)
-    FVC_TC_CASE(256, 32, 8, 5)
-    FVC_TC_CASE(256, 64, 4, 5)
-    FVC_TC_CASE(256, 128, 4, 8)
-    FVC_TC_CASE(256, 256, 2, 8)
+        return launch_tc_fwd<CI, CO, T, S, B>(a, img);
+    FVC_TC_CASE(64, 32, 8, 4, 4)
+    FVC_TC_CASE(64, 64, 4, 4, 4)
+    FVC_TC_CASE(64, 128, 4, 8, 3)
+    FVC_TC_CASE(64, 256, 2, 6, 3)
+    FVC_TC_CASE(128, 32, 8, 4, 4)
+    FVC_TC_CASE(128, 64, 4, 4, 4)
+    FVC_TC_CASE(128, 128, 4, 8, 3)
+    FVC_TC_CASE(128, 256, 2, 6, 3)
+    FVC_TC_CASE(256, 32, 8, 4, 4)
+    FVC_TC_CASE(256, 64, 4, 4, 4)
+    FVC_TC_CASE(256, 128, 4, 8, 3)
+    FVC_TC_CASE(256, 256, 2, 6, 3)
 #undef FVC_TC_CASE
     return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core kernel for channels %d -> %d", a.cin, a.cout);
 }

@@ -19,7 +19,10 @@ namespace fvc {
 
 using namespace tc;
 
-constexpr int WG_THREADS = 224;
+constexpr int WG_PRODUCER_WARPS = 8;
+constexpr int WG_PRODUCERS = WG_PRODUCER_WARPS * 32;
+constexpr int WG_WARP_MMA = WG_PRODUCER_WARPS, WG_WARP_IDX = WG_PRODUCER_WARPS + 1;
+constexpr int WG_THREADS = (WG_PRODUCER_WARPS + 2) * 32;
 constexpr int WG_IDX_RING = 8; // ring of kernel-map entries: two taps x 128 int32 per unit
 constexpr int WG_TILE = 128;
 constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 channels x 2 B
@@ -36,16 +39,16 @@ template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
-// 128 rows x 128 B into one swizzled block; 8 lanes cover one row (one full 128-byte line), 4 rows per instruction
-__device__ __forceinline__ void gather_block(uint32_t block_smem, const uint16_t *__restrict__ base, int64_t row_stride,
-                                             int col0, int idx, int warp, int lane) {
+// One warp's share (rows [16w, 16w+16)) of a 128-row x 128-byte swizzled block: 8 lanes cover one row (one full
+// 128-byte line), 4 rows per instruction; idx[i] < 0 zero-fills row 16w + 4i + (lane >> 3).
+__device__ __forceinline__ void gather_rows(uint32_t block_smem, const uint16_t *__restrict__ base, int64_t row_stride,
+                                            int col0, const int (&idx)[4], int warp, int lane) {
+    const int q = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int rl = 4 * i + (lane >> 3);
-        const int row = warp * 32 + rl, q = lane & 7;
-        const int src_idx = __shfl_sync(0xffffffffu, idx, rl);
-        const uint16_t *src = base + (src_idx >= 0 ? int64_t(src_idx) * row_stride + col0 + q * 8 : 0);
-        cp_async16(block_smem + row * 128 + ((q ^ (row & 7)) << 4), src, src_idx >= 0 ? 16u : 0u);
+    for (int i = 0; i < 4; ++i) {
+        const int row = warp * 16 + 4 * i + (lane >> 3);
+        const uint16_t *src = base + (idx[i] >= 0 ? int64_t(idx[i]) * row_stride + col0 + q * 8 : 0);
+        cp_async16(block_smem + row * 128 + ((q ^ (row & 7)) << 4), src, idx[i] >= 0 ? 16u : 0u);
     }
 }
 
@@ -100,41 +103,44 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     if (threadIdx.x == 0) {
         s_started = 0u;
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 128);
+            mbar_init(bar_full + 8 * s, WG_PRODUCERS);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_bfull + 8 * b, 128);
+            mbar_init(bar_bfull + 8 * b, WG_PRODUCERS);
             mbar_init(bar_bempty + 8 * b, 1);
         }
         mbar_init(bar_accum, 1);
         for (int e = 0; e < WG_IDX_RING; ++e) {
             mbar_init(bar_ifull + 8 * e, 32);
-            mbar_init(bar_iempty + 8 * e, 128);
+            mbar_init(bar_iempty + 8 * e, WG_PRODUCERS);
         }
         fence_mbar_init();
     }
-    if (warp == 4)
+    if (warp == WG_WARP_MMA)
         tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 4) {
-        // ================= producers: dY tile, then the gathered X blocks of every unit =================
-        const int r = threadIdx.x;
+    if (warp < WG_PRODUCER_WARPS) {
+        // ================= producers: dY tile, then the gathered X blocks of every live unit =================
+        const int rsub = lane >> 3;
         int u = 0, tb = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
-            const int64_t row = tile * WG_TILE + r;
+            const int64_t row0 = tile * WG_TILE + warp * 16 + rsub; // this lane's first row; the others are +4, +8, +12
             const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
             { // B: plain rows of dY (identity "map")
                 const int bs = tb & 1;
                 mbar_wait(bar_bempty + 8 * bs, ((tb >> 1) & 1) ^ 1);
-                const int self = row < n_out ? int(row) : -1;
+                int self[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    self[i] = row0 + 4 * i < n_out ? int(row0 + 4 * i) : -1;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb)
-                    gather_block(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES, dy, COUT, nb * 64, self, warp, lane);
+                    gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES, dy, COUT, nb * 64, self, warp, lane);
                 cp_async_arrive_noinc(bar_bfull + 8 * bs);
             }
             for (int ul = 0; ul < nunits; ++ul) {
@@ -143,18 +149,22 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 const int blk = 2 * (unit0 + ul);
                 const int e = u % WG_IDX_RING;
                 mbar_wait(bar_ifull + 8 * e, (u / WG_IDX_RING) & 1);
-                int idx0, idx1;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx0) : "r"(smem_idx + e * 1024 + r * 4) : "memory");
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1) : "r"(smem_idx + e * 1024 + 512 + r * 4) : "memory");
-                if (row >= n_out)
-                    idx0 = idx1 = -1;
-                if (blk + 1 >= total_blocks)
-                    idx1 = -1; // odd block count: the last unit's second block is a zero dummy
+                int idx0[4], idx1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t entry = smem_idx + e * 1024 + (warp * 16 + 4 * i + rsub) * 4;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx0[i]) : "r"(entry) : "memory");
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1[i]) : "r"(entry + 512) : "memory");
+                    if (row0 + 4 * i >= n_out)
+                        idx0[i] = idx1[i] = -1;
+                    if (blk + 1 >= total_blocks)
+                        idx1[i] = -1; // odd block count: the last unit's second block is a zero dummy
+                }
                 const int s = u % STAGES;
                 mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
                 const uint32_t stage = smem_a + s * Cfg::A_STAGE;
-                gather_block(stage, x, CIN, (blk % CB) * 64, idx0, warp, lane);
-                gather_block(stage + WG_BLOCK_BYTES, x, CIN, ((blk + 1) % CB) * 64, idx1, warp, lane);
+                gather_rows(stage, x, CIN, (blk % CB) * 64, idx0, warp, lane);
+                gather_rows(stage + WG_BLOCK_BYTES, x, CIN, ((blk + 1) % CB) * 64, idx1, warp, lane);
                 mbar_arrive(bar_iempty + 8 * e);
                 cp_async_arrive_noinc(bar_full + 8 * s);
                 ++u;
@@ -166,10 +176,11 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started);
-        const int half = warp >> 1;                       // which A block of the unit this warp's lanes belong to
-        const int ci_local = (warp & 1) * 32 + lane;      // channel inside the block
+        const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31
+        const int half = quarter >> 1;                    // which A block of the unit those lanes belong to
+        const int ci_local = (quarter & 1) * 32 + lane;   // channel inside the block
         float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
-        for (int ul = 0; ul < nunits; ++ul) {
+        for (int ul = warp >> 2; ul < nunits; ul += WG_PRODUCER_WARPS / 4) {
             const int blk = 2 * (unit0 + ul) + half;
             const bool live = blk < total_blocks;
             const int tap = blk / CB, ci = (blk % CB) * 64 + ci_local;
@@ -177,7 +188,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t acc[32];
                 if ((started >> ul) & 1u) {
-                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * COUT + c0), acc);
+                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ul * COUT + c0), acc);
                     tmem_ld_wait();
                 } else { // no row of this CTA's tiles ever reached these taps
 #pragma unroll
@@ -192,7 +203,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == WG_WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
             int u = 0, tb = 0;
@@ -226,7 +237,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             umma_commit(bar_accum);
         }
         __syncwarp();
-    } else if (warp == 6) {
+    } else if (warp == WG_WARP_IDX) {
         // ================= kernel-map streamer (whole warp): both taps of every live unit, 2 x 512 B =================
         int u = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
@@ -248,7 +259,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4)
+    if (warp == WG_WARP_MMA)
         tmem_dealloc(tmem_base, 512);
 }
 
