@@ -19,10 +19,9 @@ namespace fvc {
 
 using namespace tc;
 
-constexpr int WG_PRODUCER_WARPS = 8;
-constexpr int WG_PRODUCERS = WG_PRODUCER_WARPS * 32;
-constexpr int WG_WARP_MMA = WG_PRODUCER_WARPS, WG_WARP_IDX = WG_PRODUCER_WARPS + 1;
-constexpr int WG_THREADS = (WG_PRODUCER_WARPS + 2) * 32;
+constexpr int WG_PW = 4;                  // gather-producer warps (also the epilogue warps)
+constexpr int WG_WARP_MMA = WG_PW; // warp WG_PW + 1 streams the kernel map
+constexpr int WG_THREADS = (WG_PW + 2) * 32;
 constexpr int WG_IDX_RING = 8; // ring of kernel-map entries: two taps x 128 int32 per unit
 constexpr int WG_TILE = 128;
 constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 channels x 2 B
@@ -39,17 +38,15 @@ template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
-// One warp's share (rows [16w, 16w+16)) of a 128-row x 128-byte swizzled block: 8 lanes cover one row (one full
-// 128-byte line), 4 rows per instruction; idx[i] < 0 zero-fills row 16w + 4i + (lane >> 3).
-__device__ __forceinline__ void gather_rows(uint32_t block_smem, const uint16_t *__restrict__ base, int64_t row_stride,
-                                            int col0, const int (&idx)[4], int warp, int lane) {
-    const int q = lane & 7;
+// One warp's share (rows [32w, 32w+32)) of a 128-row x 128-byte swizzled block: 8 lanes cover one row (one full
+// 128-byte line), 4 rows per instruction; idx[i] < 0 zero-fills row 32w + 4i + (lane >> 3).
+__device__ __forceinline__ void gather_rows(uint32_t dst /* block + my_row * 128 */, uint32_t swz0, uint32_t swz1,
+                                            const uint16_t *__restrict__ base /* + column offset */, int64_t row_stride,
+                                            const int (&idx)[8]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = warp * 16 + 4 * i + (lane >> 3);
-        const uint16_t *src = base + (idx[i] >= 0 ? int64_t(idx[i]) * row_stride + col0 + q * 8 : 0);
-        cp_async16(block_smem + row * 128 + ((q ^ (row & 7)) << 4), src, idx[i] >= 0 ? 16u : 0u);
-    }
+    for (int i = 0; i < 8; ++i)
+        cp_async16(dst + i * 512 + ((i & 1) ? swz1 : swz0), idx[i] >= 0 ? base + int64_t(idx[i]) * row_stride : base,
+                   idx[i] >= 0 ? 16u : 0u);
 }
 
 template <int CIN, int COUT, int STAGES>
@@ -84,36 +81,37 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     const int64_t tile_end = tile_begin + tiles_per_chunk < total_tiles ? tile_begin + tiles_per_chunk : total_tiles;
 
     // (tile, unit) skipping: a unit is live for a tile iff one of its (at most two) taps reaches a row of the tile.
-    // Both roles evaluate the same predicate from the tile's tap bitmask (K^3 <= 128; larger kernels do not skip).
+    // Every role derives the same live-unit bitmask from the tile's tap bitmask (K^3 <= 128; larger kernels do not skip).
     const int words = (k3 + 63) >> 6;
     const bool use_mask = tile_mask != nullptr && words <= 2;
-    auto unit_live = [&](unsigned long long m0, unsigned long long m1, int ul) -> bool {
+    auto live_units = [&](int64_t tile) -> uint32_t {
         if (!use_mask)
-            return true;
-        const int blk = 2 * (unit0 + ul);
-        const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
-        const unsigned long long bit_a = ((ta < 64 ? m0 : m1) >> (ta & 63)) & 1ull;
-        const unsigned long long bit_b = ((tb_ < 64 ? m0 : m1) >> (tb_ & 63)) & 1ull;
-        return (bit_a | bit_b) != 0ull;
-    };
-    auto load_mask = [&](int64_t tile, int w) -> unsigned long long {
-        return (use_mask && w < words) ? __ldg(tile_mask + tile * words + w) : 0ull;
+            return (1u << nunits) - 1u;
+        const unsigned long long m0 = __ldg(tile_mask + tile * words), m1 = words > 1 ? __ldg(tile_mask + tile * words + 1) : 0ull;
+        uint32_t live = 0;
+        for (int ul = 0; ul < nunits; ++ul) {
+            const int blk = 2 * (unit0 + ul);
+            const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
+            const unsigned long long bit = (((ta < 64 ? m0 : m1) >> (ta & 63)) | ((tb_ < 64 ? m0 : m1) >> (tb_ & 63))) & 1ull;
+            live |= uint32_t(bit) << ul;
+        }
+        return live;
     };
 
     if (threadIdx.x == 0) {
         s_started = 0u;
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, WG_PRODUCERS);
+            mbar_init(bar_full + 8 * s, WG_PW * 32);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_bfull + 8 * b, WG_PRODUCERS);
+            mbar_init(bar_bfull + 8 * b, WG_PW * 32);
             mbar_init(bar_bempty + 8 * b, 1);
         }
         mbar_init(bar_accum, 1);
         for (int e = 0; e < WG_IDX_RING; ++e) {
             mbar_init(bar_ifull + 8 * e, 32);
-            mbar_init(bar_iempty + 8 * e, WG_PRODUCERS);
+            mbar_init(bar_iempty + 8 * e, WG_PW);
         }
         fence_mbar_init();
     }
@@ -124,50 +122,63 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < WG_PRODUCER_WARPS) {
+    if (warp < WG_PW) {
         // ================= producers: dY tile, then the gathered X blocks of every live unit =================
-        const int rsub = lane >> 3;
-        int u = 0, tb = 0;
+        const int q = lane & 7;
+        const int my_row = warp * 32 + (lane >> 3); // rows my_row + 4i, i < 8
+        const uint32_t dst0 = uint32_t(my_row) * 128u;
+        const uint32_t swz0 = uint32_t(q ^ (my_row & 7)) << 4, swz1 = uint32_t(q ^ ((my_row & 7) ^ 4)) << 4;
+        const uint16_t *xq = x + q * 8, *dyq = dy + q * 8;
+        int s = 0, e = 0, tb = 0;
+        uint32_t ph = 0, eph = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
-            const int64_t row0 = tile * WG_TILE + warp * 16 + rsub; // this lane's first row; the others are +4, +8, +12
-            const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
+            const int64_t rows_left = n_out - tile * WG_TILE - my_row; // row my_row + 4i exists iff 4i < rows_left
+            const uint32_t live = live_units(tile);
             { // B: plain rows of dY (identity "map")
                 const int bs = tb & 1;
                 mbar_wait(bar_bempty + 8 * bs, ((tb >> 1) & 1) ^ 1);
-                int self[4];
+                int self[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    self[i] = row0 + 4 * i < n_out ? int(row0 + 4 * i) : -1;
+                for (int i = 0; i < 8; ++i)
+                    self[i] = 4 * i < rows_left ? int(tile * WG_TILE + my_row + 4 * i) : -1;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb)
-                    gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES, dy, COUT, nb * 64, self, warp, lane);
+                    gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES + dst0, swz0, swz1, dyq + nb * 64, COUT, self);
                 cp_async_arrive_noinc(bar_bfull + 8 * bs);
             }
-            for (int ul = 0; ul < nunits; ++ul) {
-                if (!unit_live(m0, m1, ul))
-                    continue;
-                const int blk = 2 * (unit0 + ul);
-                const int e = u % WG_IDX_RING;
-                mbar_wait(bar_ifull + 8 * e, (u / WG_IDX_RING) & 1);
-                int idx0[4], idx1[4];
+            for (uint32_t rest = live; rest; rest &= rest - 1u) {
+                const int blk = 2 * (unit0 + __ffs(rest) - 1);
+                mbar_wait(bar_ifull + 8 * e, eph);
+                int idx0[8], idx1[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t entry = smem_idx + e * 1024 + (warp * 16 + 4 * i + rsub) * 4;
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t entry = smem_idx + e * 1024 + (my_row + 4 * i) * 4;
                     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx0[i]) : "r"(entry) : "memory");
                     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1[i]) : "r"(entry + 512) : "memory");
-                    if (row0 + 4 * i >= n_out)
+                    if (4 * i >= rows_left)
                         idx0[i] = idx1[i] = -1;
-                    if (blk + 1 >= total_blocks)
-                        idx1[i] = -1; // odd block count: the last unit's second block is a zero dummy
                 }
-                const int s = u % STAGES;
-                mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1);
-                const uint32_t stage = smem_a + s * Cfg::A_STAGE;
-                gather_rows(stage, x, CIN, (blk % CB) * 64, idx0, warp, lane);
-                gather_rows(stage + WG_BLOCK_BYTES, x, CIN, ((blk + 1) % CB) * 64, idx1, warp, lane);
-                mbar_arrive(bar_iempty + 8 * e);
+                if (blk + 1 >= total_blocks) { // odd block count: the last unit's second block is a zero dummy
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        idx1[i] = -1;
+                }
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
+                gather_rows(stage, swz0, swz1, xq + (blk % CB) * 64, CIN, idx0);
+                gather_rows(stage + WG_BLOCK_BYTES, swz0, swz1, xq + ((blk + 1) % CB) * 64, CIN, idx1);
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(bar_iempty + 8 * e);
                 cp_async_arrive_noinc(bar_full + 8 * s);
-                ++u;
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+                if (++e == WG_IDX_RING) {
+                    e = 0;
+                    eph ^= 1u;
+                }
             }
         }
         cp_async_wait_all();
@@ -176,11 +187,10 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started);
-        const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31
-        const int half = quarter >> 1;                    // which A block of the unit those lanes belong to
-        const int ci_local = (quarter & 1) * 32 + lane;   // channel inside the block
+        const int half = warp >> 1;                   // which A block of the unit this warp's TMEM lanes belong to
+        const int ci_local = (warp & 1) * 32 + lane;  // channel inside the block
         float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
-        for (int ul = warp >> 2; ul < nunits; ul += WG_PRODUCER_WARPS / 4) {
+        for (int ul = 0; ul < nunits; ++ul) {
             const int blk = 2 * (unit0 + ul) + half;
             const bool live = blk < total_blocks;
             const int tap = blk / CB, ci = (blk % CB) * 64 + ci_local;
@@ -188,12 +198,12 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t acc[32];
                 if ((started >> ul) & 1u) {
-                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ul * COUT + c0), acc);
+                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * COUT + c0), acc);
                     tmem_ld_wait();
                 } else { // no row of this CTA's tiles ever reached these taps
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        acc[e] = 0u;
+                    for (int z = 0; z < 32; ++z)
+                        acc[z] = 0u;
                 }
                 if (live) {
                     uint4 *dst = reinterpret_cast<uint4 *>(slice + (int64_t(tap) * CIN + ci) * COUT + c0);
@@ -206,29 +216,33 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     } else if (warp == WG_WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            int u = 0, tb = 0;
-            uint32_t started = 0;
+            // MN-major SWIZZLE_128B descriptors: LBO = distance between the two 64-channel blocks, SBO = 8-row group
+            const uint64_t desc_hi = make_smem_desc_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFF00000000ull;
+            const uint32_t lbo = uint32_t(WG_BLOCK_BYTES >> 4) << 16;
+            const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | lbo;
+            int s = 0, tb = 0;
+            uint32_t ph = 0, started = 0;
             for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
                 const int bs = tb & 1;
-                const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
+                const uint32_t live = live_units(tile);
                 mbar_wait(bar_bfull + 8 * bs, (tb >> 1) & 1);
-                const uint32_t b_base = smem_b + bs * Cfg::B_STAGE;
-                for (int ul = 0; ul < nunits; ++ul) {
-                    if (!unit_live(m0, m1, ul))
-                        continue;
-                    const int s = u % STAGES;
-                    mbar_wait(bar_full + 8 * s, (u / STAGES) & 1);
+                const uint32_t b_lo = b_lo0 + uint32_t(bs) * (Cfg::B_STAGE >> 4);
+                for (uint32_t rest = live; rest; rest &= rest - 1u) {
+                    const int ul = __ffs(rest) - 1;
+                    mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t a_base = smem_a + s * Cfg::A_STAGE;
+                    const uint32_t a_lo = a_lo0 + uint32_t(s) * (Cfg::A_STAGE >> 4);
+                    const uint32_t acc0 = (started >> ul) & 1u;
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) // 16 rows (K) per MMA = two 8-row swizzle groups = 2048 B
-                        umma_f16(tmem_base + uint32_t(ul * COUT),
-                                 make_smem_desc_sw128(a_base + kk * 2048, WG_BLOCK_BYTES, 1024),
-                                 make_smem_desc_sw128(b_base + kk * 2048, WG_BLOCK_BYTES, 1024), idesc,
-                                 ((started >> ul) & 1u) | uint32_t(kk != 0));
+                    for (int kk = 0; kk < 8; ++kk) // 16 rows (K) per MMA = two 8-row swizzle groups = 2048 B = 128 units
+                        umma_f16(tmem_base + uint32_t(ul * COUT), desc_hi | (a_lo + 128 * kk), desc_hi | (b_lo + 128 * kk), idesc,
+                                 acc0 | uint32_t(kk != 0));
                     umma_commit(bar_empty + 8 * s);
                     started |= 1u << ul;
-                    ++u;
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
                 umma_commit(bar_bempty + 8 * bs);
             }
@@ -237,22 +251,24 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             umma_commit(bar_accum);
         }
         __syncwarp();
-    } else if (warp == WG_WARP_IDX) {
+    } else {
         // ================= kernel-map streamer (whole warp): both taps of every live unit, 2 x 512 B =================
-        int u = 0;
+        int e = 0;
+        uint32_t eph = 0;
+        const int32_t *lane_nbr = nbr + lane * 4;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-            const unsigned long long m0 = load_mask(tile, 0), m1 = load_mask(tile, 1);
-            for (int ul = 0; ul < nunits; ++ul) {
-                if (!unit_live(m0, m1, ul))
-                    continue;
-                const int blk = 2 * (unit0 + ul);
+            const uint32_t live = live_units(tile);
+            for (uint32_t rest = live; rest; rest &= rest - 1u) {
+                const int blk = 2 * (unit0 + __ffs(rest) - 1);
                 const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
-                const int e = u % WG_IDX_RING;
-                mbar_wait(bar_iempty + 8 * e, ((u / WG_IDX_RING) & 1) ^ 1);
-                cp_async16(smem_idx + e * 1024 + lane * 16, nbr + int64_t(ta) * pitch + tile * WG_TILE + lane * 4, 16u);
-                cp_async16(smem_idx + e * 1024 + 512 + lane * 16, nbr + int64_t(tb_) * pitch + tile * WG_TILE + lane * 4, 16u);
+                mbar_wait(bar_iempty + 8 * e, eph ^ 1u);
+                cp_async16(smem_idx + e * 1024 + lane * 16, lane_nbr + int64_t(ta) * pitch + tile * WG_TILE, 16u);
+                cp_async16(smem_idx + e * 1024 + 512 + lane * 16, lane_nbr + int64_t(tb_) * pitch + tile * WG_TILE, 16u);
                 cp_async_arrive_noinc(bar_ifull + 8 * e);
-                ++u;
+                if (++e == WG_IDX_RING) {
+                    e = 0;
+                    eph ^= 1u;
+                }
             }
         }
         cp_async_wait_all();
