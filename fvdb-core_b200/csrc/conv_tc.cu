@@ -36,40 +36,52 @@ constexpr int TC_MAX_UNITS = 4096;          // capacity of the per-CTA unit list
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
+// Small channel counts are packed: a 64-wide reduction block holds G = 64 / CIN consecutive taps x CIN channels
+// ("tap group"), so Cin = 16 / 32 feed the same K = 64 pipeline (the bandwidth-bound small-channel path).
 template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW> struct TcFwdCfg {
-    static constexpr int KB = CIN / 64;                      // 64-channel reduction blocks per tap
+    static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per reduction block
+    static constexpr int KB = CIN >= 64 ? CIN / 64 : 1;     // 64-wide reduction blocks per tap group
+    static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a 128-byte row
     static constexpr int B_BYTES = COUT * 128;               // one weight chunk: COUT rows x 64 channels x 2 B
     static constexpr int TMEM_COLS = tmem_cols_for(TILES * COUT);
     static constexpr int THREADS = (PW + 3) * 32;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * BST + 1 + 2 * TC_IDX_RING;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TC_IDX_RING) * 512 +
+    static constexpr int RING_BYTES = G * 512;               // one ring entry: 128 map entries per tap of the group
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TC_IDX_RING) * RING_BYTES +
                                    size_t(TC_MAX_UNITS) * 2 + 8 * NUM_BARS + 16;
     // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (228 KB per SM, 1 KB reserved per CTA)
     static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = int(233472 / (SMEM + 1024 + 768));
     static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > 2 ? 2 : BY_TMEM) : (BY_SMEM > 2 ? 2 : BY_SMEM);
     static_assert(CTAS_PER_SM >= 1, "configuration does not fit one SM");
-    static_assert(CIN % 64 == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
+    static_assert((CIN % 64 == 0 || CIN == 32 || CIN == 16) && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * COUT <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
     static_assert(PW == 4 || PW == 8, "producer warps");
 };
 
-// Weight image: for chunk c = tap * KB + j, COUT rows of 128 B; row n holds channels [64j, 64j+64) of
-// W[tap][:, n] with 16-byte chunk q stored at position q ^ (n & 7)  (the SWIZZLE_128B K-major atom).
+// Weight image: chunk c = group * KB + j holds COUT rows of 128 B; row n = the 64 reduction elements of that chunk for
+// output channel n (Cin >= 64: channels [64j, 64j+64) of tap `group`; Cin < 64: taps [G*group, G*group+G) x Cin
+// channels, zero beyond the last tap), 16-byte chunk q stored at position q ^ (n & 7) (SWIZZLE_128B K-major atom).
 __global__ void tc_pack_b_kernel(const uint16_t *__restrict__ w /*[k3][cin][cout]*/, int k3, int cin, int cout,
                                  uint4 *__restrict__ img) {
-    const int kb = cin / 64;
-    const int64_t total = int64_t(k3) * kb * cout * 8; // 16-byte chunks
+    const int g = cin >= 64 ? 1 : 64 / cin, kb = cin >= 64 ? cin / 64 : 1;
+    const int groups = (k3 + g - 1) / g;
+    const int64_t total = int64_t(groups) * kb * cout * 8; // 16-byte chunks
     for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
         const int pos = int(e & 7);
         const int n = int((e >> 3) % cout);
         const int64_t chunk = (e >> 3) / cout;
-        const int j = int(chunk % kb), tap = int(chunk / kb);
+        const int j = int(chunk % kb), group = int(chunk / kb);
         const int q = pos ^ (n & 7);
-        const uint16_t *src = w + (int64_t(tap) * cin + j * 64 + q * 8) * cout + n;
-        uint32_t v[4];
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        const int kk0 = q * 8; // first of the 8 reduction elements of this 16-byte chunk
+        const int tap = cin >= 64 ? group : group * g + kk0 / cin;
+        const int ci0 = cin >= 64 ? j * 64 + kk0 : kk0 % cin;
+        if (tap < k3) {
+            const uint16_t *src = w + (int64_t(tap) * cin + ci0) * cout + n;
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
-            v[h] = uint32_t(src[int64_t(2 * h) * cout]) | (uint32_t(src[int64_t(2 * h + 1) * cout]) << 16);
+            for (int h = 0; h < 4; ++h)
+                v[h] = uint32_t(src[int64_t(2 * h) * cout]) | (uint32_t(src[int64_t(2 * h + 1) * cout]) << 16);
+        }
         img[e] = make_uint4(v[0], v[1], v[2], v[3]);
     }
 }
@@ -92,14 +104,14 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                    uint16_t *__restrict__ y, const int32_t *__restrict__ nbr, int64_t pitch,
                    const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, uint32_t idesc, int is_bf16) {
     using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW>;
-    constexpr int KB = Cfg::KB, THREADS = Cfg::THREADS;
+    constexpr int KB = Cfg::KB, G = Cfg::G, CPT = Cfg::CPT, THREADS = Cfg::THREADS;
     constexpr int WARP_MMA = PW, WARP_B = PW + 1;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
     const uint32_t smem_idx = smem_b + BST * Cfg::B_BYTES;
-    const uint32_t smem_units = smem_idx + TC_IDX_RING * 512;
+    const uint32_t smem_units = smem_idx + TC_IDX_RING * Cfg::RING_BYTES;
     const uint32_t bars = smem_units + TC_MAX_UNITS * 2;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 8 * BST;
@@ -115,18 +127,24 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const int64_t tile0 = int64_t(blockIdx.x) * TILES;
     const int ntiles = int(total_tiles - tile0 < TILES ? total_tiles - tile0 : TILES);
 
-    // ---- prologue: which tiles does each tap reach (bit t of s_tiles[k]), then the ordered list of live units ----
+    // ---- prologue: which tiles does each tap group reach (bit t of s_tiles[g]), then the ordered list of live units ----
     __shared__ uint8_t s_tiles[64 * TC_MASK_WORDS];
     __shared__ int s_nunits, s_live;
+    const int ngroups = (k3 + G - 1) / G;
     {
         const int words = (k3 + 63) >> 6;
-        for (int k = threadIdx.x; k < k3; k += THREADS) {
+        for (int g = threadIdx.x; g < ngroups; g += THREADS) {
             uint32_t bits = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const unsigned long long m = tile_mask ? __ldg(tile_mask + (tile0 + t) * words + (k >> 6)) : ~0ull;
-                bits |= uint32_t((m >> (k & 63)) & 1ull) << t;
+            for (int sub = 0; sub < G; ++sub) {
+                const int k = g * G + sub;
+                if (k >= k3)
+                    break;
+                for (int t = 0; t < ntiles; ++t) {
+                    const unsigned long long m = tile_mask ? __ldg(tile_mask + (tile0 + t) * words + (k >> 6)) : ~0ull;
+                    bits |= uint32_t((m >> (k & 63)) & 1ull) << t;
+                }
             }
-            s_tiles[k] = uint8_t(bits);
+            s_tiles[g] = uint8_t(bits);
         }
     }
     if (threadIdx.x == 0) {
@@ -148,12 +166,12 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     if (warp == WARP_MMA)
         tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     __syncthreads();
-    if (warp == 0) { // unit list in [tap][channel block][tile] order: entry = tap << 5 | block << 3 | tile
+    if (warp == 0) { // unit list in [tap group][channel block][tile] order: entry = group << 5 | block << 3 | tile
         int base = 0;
         uint32_t live = 0;
-        for (int k0 = 0; k0 < k3; k0 += 32) {
+        for (int k0 = 0; k0 < ngroups; k0 += 32) {
             const int k = k0 + lane;
-            const uint32_t bits = k < k3 ? s_tiles[k] : 0u;
+            const uint32_t bits = k < ngroups ? s_tiles[k] : 0u;
             const int cnt = KB * __popc(bits);
             int incl = cnt;
 #pragma unroll
@@ -190,19 +208,23 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         const int my_row = warp * RPW + (lane >> 3);          // rows my_row + 4i, i < NI
         const uint32_t dst0 = uint32_t(my_row) * 128u;
         const uint32_t swz0 = uint32_t(q ^ (my_row & 7)) << 4, swz1 = uint32_t(q ^ ((my_row & 7) ^ 4)) << 4;
-        const uint16_t *xq = x + q * 8;
+        // lane q copies 16-byte chunk q of each of its rows; with packed taps (Cin < 64) that chunk belongs to tap
+        // `sub` of the group and to channel chunk q % CPT of that tap's feature row
+        const int sub = q / CPT;
+        const uint16_t *xq = x + (CIN >= 64 ? q * 8 : (q % CPT) * 8);
         int s = 0;
         uint32_t ph = 0;
         for (int u = 0; u < nunits; ++u) {
             const uint32_t unit = units[u];
-            const int j = (unit >> 3) & 3, t = unit & 7;
+            const int g = int(unit >> 5), j = (unit >> 3) & 3, t = unit & 7;
             const int e = u & (TC_IDX_RING - 1);
             mbar_wait(bar_ifull + 8 * e, (u / TC_IDX_RING) & 1);
             int idx[NI];
 #pragma unroll
             for (int i = 0; i < NI; ++i)
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx[i]) : "r"(smem_idx + e * 512 + (my_row + 4 * i) * 4) : "memory");
-            const int64_t rows_left = n_out - (tile0 + t) * TC_TILE_M - my_row; // row my_row + 4i exists iff 4i < rows_left
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx[i]) : "r"(smem_idx + e * Cfg::RING_BYTES + sub * 512 + (my_row + 4 * i) * 4) : "memory");
+            // row my_row + 4i exists iff 4i < rows_left; a tap beyond the kernel volume (last, partial group) is empty
+            const int64_t rows_left = (G == 1 || g * G + sub < k3) ? n_out - (tile0 + t) * TC_TILE_M - my_row : 0;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             const uint32_t dst = smem_a + s * TC_A_BYTES + dst0;
             const uint16_t *xj = xq + j * 64;
@@ -232,11 +254,16 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         const uint32_t live = uint32_t(s_live);
         for (int tt = warp >> 2; tt < ntiles; tt += PW / 4) {
             const int64_t row = (tile0 + tt) * TC_TILE_M + quarter * 32 + lane;
+            constexpr int EC = COUT >= 32 ? 32 : 16; // columns drained per tcgen05.ld
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
+            for (int c0 = 0; c0 < COUT; c0 += EC) {
                 uint32_t acc[32];
                 if ((live >> tt) & 1u) {
-                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(tt * COUT + c0), acc);
+                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(tt * COUT + c0);
+                    if (EC == 32)
+                        tmem_ld_32x32b_x32(taddr, acc);
+                    else
+                        tmem_ld_32x32b_x16(taddr, acc);
                     tmem_ld_wait();
                 } else { // a tile no tap reaches was never accumulated: its rows are zero (+ bias)
 #pragma unroll
@@ -246,7 +273,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 if (row < n_out) {
                     uint4 *dst = reinterpret_cast<uint4 *>(y + row * COUT + c0);
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
+                    for (int v4 = 0; v4 < EC / 8; ++v4) {
                         uint32_t p[4];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
@@ -323,10 +350,13 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         const int32_t *lane_nbr = nbr + tile0 * TC_TILE_M + lane * 4;
         for (int u = 0; u < nunits; ++u) {
             const uint32_t unit = units[u];
-            const int k = int(unit >> 5), t = unit & 7;
+            const int g = int(unit >> 5), t = unit & 7;
             const int e = u & (TC_IDX_RING - 1);
             mbar_wait(bar_iempty + 8 * e, ((u / TC_IDX_RING) & 1) ^ 1);
-            cp_async16(smem_idx + e * 512 + lane * 16, lane_nbr + int64_t(k) * pitch + t * TC_TILE_M, 16u);
+#pragma unroll
+            for (int sub = 0; sub < G; ++sub)
+                if (g * G + sub < k3)
+                    cp_async16(smem_idx + e * Cfg::RING_BYTES + sub * 512 + lane * 16, lane_nbr + int64_t(g * G + sub) * pitch + t * TC_TILE_M, 16u);
             cp_async_arrive_noinc(bar_ifull + 8 * e);
         }
         cp_async_wait_all();
@@ -346,7 +376,7 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW> static int 
         FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
         configured = true;
     }
-    FVC_REQUIRE(int64_t(a.k3) * Cfg::KB * TILES <= TC_MAX_UNITS, FVC_ERR_UNSUPPORTED, "kernel volume %d too large for the tensor-core unit list", a.k3);
+    FVC_REQUIRE(ceil_div(a.k3, Cfg::G) * Cfg::KB * TILES <= TC_MAX_UNITS, FVC_ERR_UNSUPPORTED, "kernel volume %d too large for the tensor-core unit list", a.k3);
     const int64_t tiles = ceil_div(a.n_out, TC_TILE_M);
     const unsigned grid = unsigned(ceil_div(tiles, TILES));
     const bool bf16 = a.dtype == FVC_BF16;
@@ -359,18 +389,22 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW> static int 
     return FVC_OK;
 }
 
+static inline int tc_groups(int64_t k3, int32_t cin) { return cin >= 64 ? int(k3) : int(ceil_div(k3, 64 / cin)); }
+
 bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
     if (dtype != FVC_F16 && dtype != FVC_BF16)
         return false;
-    if (k3 < 1 || k3 > 64 * TC_MASK_WORDS || k3 * int64_t(cin / 64) * 8 > TC_MAX_UNITS)
+    const bool cin_ok = cin == 16 || cin == 32 || cin == 64 || cin == 128 || cin == 256;
+    const bool cout_ok = cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256;
+    if (!cin_ok || !cout_ok)
         return false;
-    const bool cin_ok = cin == 64 || cin == 128 || cin == 256;
-    const bool cout_ok = cout == 32 || cout == 64 || cout == 128 || cout == 256;
-    return cin_ok && cout_ok;
+    const int64_t kb = cin >= 64 ? cin / 64 : 1;
+    return k3 >= 1 && k3 <= 64 * TC_MASK_WORDS && tc_groups(k3, cin) * kb * 8 <= TC_MAX_UNITS;
 }
 
 size_t tc_forward_scratch_bytes(int64_t, int32_t cin, int32_t cout, int64_t k3, int32_t) {
-    return size_t(k3) * size_t(cin) * size_t(cout) * 2 + 256;
+    const int64_t kb = cin >= 64 ? cin / 64 : 1;
+    return size_t(tc_groups(k3, cin)) * size_t(kb) * size_t(cout) * 128 + 256;
 }
 
 int tc_forward(const ConvArgs &a) {
@@ -383,7 +417,7 @@ int tc_forward(const ConvArgs &a) {
     FVC_REQUIRE(a.pitch % 4 == 0 && a.pitch >= ceil_div(a.n_out, TC_TILE_M) * TC_TILE_M, FVC_ERR_RUNTIME,
                 "tensor-core conv needs the map pitch (%lld) to be a multiple of 4 covering whole 128-row tiles", (long long)a.pitch);
     uint8_t *img = reinterpret_cast<uint8_t *>(a.scratch);
-    const int64_t chunks16 = int64_t(a.k3) * a.cin * a.cout / 8;
+    const int64_t chunks16 = int64_t(tc_groups(a.k3, a.cin)) * (a.cin >= 64 ? a.cin / 64 : 1) * a.cout * 8;
     tc_pack_b_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
         reinterpret_cast<const uint16_t *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
     FVC_LAUNCH_CHECK();
@@ -401,18 +435,18 @@ int tc_forward(const ConvArgs &a) {
 #define FVC_TC_CASE(CI, CO, T, S, B) \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_fwd<CI, CO, T, S, B, 4>(a, img);
-    FVC_TC_CASE(64, 32, 8, 4, 3)
-    FVC_TC_CASE(64, 64, 4, 4, 3)
-    FVC_TC_CASE(64, 128, 4, 8, 3)
-    FVC_TC_CASE(64, 256, 2, 6, 3)
-    FVC_TC_CASE(128, 32, 8, 4, 3)
-    FVC_TC_CASE(128, 64, 4, 4, 3)
-    FVC_TC_CASE(128, 128, 4, 8, 3)
-    FVC_TC_CASE(128, 256, 2, 6, 3)
-    FVC_TC_CASE(256, 32, 8, 4, 3)
-    FVC_TC_CASE(256, 64, 4, 4, 3)
-    FVC_TC_CASE(256, 128, 4, 8, 3)
-    FVC_TC_CASE(256, 256, 2, 6, 3)
+#define FVC_TC_CIN(CI)           \
+    FVC_TC_CASE(CI, 16, 8, 4, 3)  \
+    FVC_TC_CASE(CI, 32, 8, 4, 3)  \
+    FVC_TC_CASE(CI, 64, 4, 4, 3)  \
+    FVC_TC_CASE(CI, 128, 4, 8, 3) \
+    FVC_TC_CASE(CI, 256, 2, 6, 3)
+    FVC_TC_CIN(16)
+    FVC_TC_CIN(32)
+    FVC_TC_CIN(64)
+    FVC_TC_CIN(128)
+    FVC_TC_CIN(256)
+#undef FVC_TC_CIN
 #undef FVC_TC_CASE
     return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core kernel for channels %d -> %d", a.cin, a.cout);
 }

@@ -20,21 +20,29 @@ namespace fvc {
 using namespace tc;
 
 constexpr int WG_PW = 4;                  // gather-producer warps (also the epilogue warps)
-constexpr int WG_WARP_MMA = WG_PW; // warp WG_PW + 1 streams the kernel map
+constexpr int WG_WARP_MMA = WG_PW;        // warp WG_PW + 1 streams the kernel map
 constexpr int WG_THREADS = (WG_PW + 2) * 32;
-constexpr int WG_IDX_RING = 8; // ring of kernel-map entries: two taps x 128 int32 per unit
 constexpr int WG_TILE = 128;
-constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 channels x 2 B
+constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 reduction-side elements x 2 B
 
+// Small channel counts are packed like in the forward kernel: an A block holds G = 64 / CIN taps x CIN channels;
+// a dY row narrower than 64 channels is zero-padded to one 128-byte row (N = 64 for the MMA, extra columns unused).
 template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
-    static constexpr int CB = CIN / 64;            // A channel blocks per tap
-    static constexpr int NB = COUT / 64;           // B channel blocks
-    static constexpr int MAX_UNITS = 512 / COUT;   // accumulators that fit TMEM
+    static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per A block
+    static constexpr int CB = CIN >= 64 ? CIN / 64 : 1;     // A channel blocks per tap (group)
+    static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a row
+    static constexpr int NB = COUT >= 64 ? COUT / 64 : 1;   // B blocks
+    static constexpr int NPAD = COUT >= 64 ? COUT : 64;     // MMA N = TMEM columns per unit
+    static constexpr int BQ = COUT >= 64 ? 8 : COUT / 8;    // valid 16-byte chunks of a dY row per B block
+    static constexpr int MAX_UNITS = 512 / NPAD;            // accumulators that fit TMEM
+    static constexpr int RING = G == 4 ? 4 : 8;             // kernel-map ring depth
+    static constexpr int RING_BYTES = 2 * G * 512;          // two blocks x G taps x 128 int32
     static constexpr int A_STAGE = 2 * WG_BLOCK_BYTES;
     static constexpr int B_STAGE = NB * WG_BLOCK_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * WG_IDX_RING;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + 2 * size_t(B_STAGE) + size_t(WG_IDX_RING) * 1024 + 8 * NUM_BARS + 16;
-    static_assert(CIN % 64 == 0 && COUT % 64 == 0 && CIN <= 256 && COUT <= 256, "unsupported channel counts");
+    static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * RING;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + 2 * size_t(B_STAGE) + size_t(RING) * RING_BYTES + 8 * NUM_BARS + 16;
+    static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128 || CIN == 256, "unsupported Cin");
+    static_assert(COUT == 16 || COUT == 32 || COUT == 64 || COUT == 128 || COUT == 256, "unsupported Cout");
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -55,33 +63,35 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                      int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
                      int tiles_per_chunk, uint32_t idesc, float *__restrict__ partial) {
     using Cfg = TcWgradCfg<CIN, COUT, STAGES>;
-    constexpr int CB = Cfg::CB, NB = Cfg::NB;
+    constexpr int G = Cfg::G, CB = Cfg::CB, CPT = Cfg::CPT, NB = Cfg::NB, NPAD = Cfg::NPAD, RING = Cfg::RING;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * Cfg::A_STAGE;
     const uint32_t smem_idx = smem_b + 2 * Cfg::B_STAGE;
-    const uint32_t bars = smem_idx + WG_IDX_RING * 1024;
+    const uint32_t bars = smem_idx + RING * Cfg::RING_BYTES;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
     const uint32_t bar_accum = bar_bempty + 16;
-    const uint32_t bar_ifull = bar_accum + 8, bar_iempty = bar_ifull + 8 * WG_IDX_RING;
-    const uint32_t tmem_slot = bar_iempty + 8 * WG_IDX_RING;
+    const uint32_t bar_ifull = bar_accum + 8, bar_iempty = bar_ifull + 8 * RING;
+    const uint32_t tmem_slot = bar_iempty + 8 * RING;
     __shared__ uint32_t s_started; // units whose accumulator was written at least once (MMA thread -> epilogue)
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_blocks = k3 * CB;
+    // A block b: Cin >= 64 -> (tap b / CB, channels 64 * (b % CB) ..); Cin < 64 -> taps [G b, G b + G) x all channels
+    const int total_blocks = CIN >= 64 ? k3 * CB : (k3 + G - 1) / G;
     const int total_units = (total_blocks + 1) / 2;
     const int unit0 = blockIdx.y * units_per_group;
     const int nunits = total_units - unit0 < units_per_group ? total_units - unit0 : units_per_group;
     const int64_t total_tiles = (n_out + WG_TILE - 1) / WG_TILE;
     const int64_t tile_begin = int64_t(blockIdx.x) * tiles_per_chunk;
     const int64_t tile_end = tile_begin + tiles_per_chunk < total_tiles ? tile_begin + tiles_per_chunk : total_tiles;
+    auto first_tap = [&](int blk) -> int { return CIN >= 64 ? blk / CB : blk * G; };
 
-    // (tile, unit) skipping: a unit is live for a tile iff one of its (at most two) taps reaches a row of the tile.
-    // Every role derives the same live-unit bitmask from the tile's tap bitmask (K^3 <= 128; larger kernels do not skip).
+    // (tile, unit) skipping: a unit is live for a tile iff one of its taps reaches a row of the tile.  Every role derives
+    // the same live-unit bitmask from the tile's tap bitmask (K^3 <= 128; larger kernels do not skip).
     const int words = (k3 + 63) >> 6;
     const bool use_mask = tile_mask != nullptr && words <= 2;
     auto live_units = [&](int64_t tile) -> uint32_t {
@@ -91,9 +101,13 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         uint32_t live = 0;
         for (int ul = 0; ul < nunits; ++ul) {
             const int blk = 2 * (unit0 + ul);
-            const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
-            const unsigned long long bit = (((ta < 64 ? m0 : m1) >> (ta & 63)) | ((tb_ < 64 ? m0 : m1) >> (tb_ & 63))) & 1ull;
-            live |= uint32_t(bit) << ul;
+            const int t_lo = first_tap(blk);
+            int t_hi = first_tap(blk + 1 < total_blocks ? blk + 1 : blk) + G; // exclusive
+            t_hi = t_hi < k3 ? t_hi : k3;
+            unsigned long long any = 0ull;
+            for (int tap = t_lo; tap < t_hi; ++tap)
+                any |= ((tap < 64 ? m0 : m1) >> (tap & 63)) & 1ull;
+            live |= uint32_t(any) << ul;
         }
         return live;
     };
@@ -109,7 +123,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             mbar_init(bar_bempty + 8 * b, 1);
         }
         mbar_init(bar_accum, 1);
-        for (int e = 0; e < WG_IDX_RING; ++e) {
+        for (int e = 0; e < RING; ++e) {
             mbar_init(bar_ifull + 8 * e, 32);
             mbar_init(bar_iempty + 8 * e, WG_PW);
         }
@@ -124,23 +138,23 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
 
     if (warp < WG_PW) {
         // ================= producers: dY tile, then the gathered X blocks of every live unit =================
-        const int q = lane & 7;
+        const int q = lane & 7, sub = q / CPT;
         const int my_row = warp * 32 + (lane >> 3); // rows my_row + 4i, i < 8
         const uint32_t dst0 = uint32_t(my_row) * 128u;
         const uint32_t swz0 = uint32_t(q ^ (my_row & 7)) << 4, swz1 = uint32_t(q ^ ((my_row & 7) ^ 4)) << 4;
-        const uint16_t *xq = x + q * 8, *dyq = dy + q * 8;
+        const uint16_t *xq = x + (CIN >= 64 ? q * 8 : (q % CPT) * 8), *dyq = dy + q * 8;
         int s = 0, e = 0, tb = 0;
         uint32_t ph = 0, eph = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
             const int64_t rows_left = n_out - tile * WG_TILE - my_row; // row my_row + 4i exists iff 4i < rows_left
             const uint32_t live = live_units(tile);
-            { // B: plain rows of dY (identity "map")
+            { // B: plain rows of dY (identity "map"); lanes beyond a narrow row's chunks zero-fill
                 const int bs = tb & 1;
                 mbar_wait(bar_bempty + 8 * bs, ((tb >> 1) & 1) ^ 1);
                 int self[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    self[i] = 4 * i < rows_left ? int(tile * WG_TILE + my_row + 4 * i) : -1;
+                    self[i] = (4 * i < rows_left && q < Cfg::BQ) ? int(tile * WG_TILE + my_row + 4 * i) : -1;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb)
                     gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES + dst0, swz0, swz1, dyq + nb * 64, COUT, self);
@@ -150,23 +164,22 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 const int blk = 2 * (unit0 + __ffs(rest) - 1);
                 mbar_wait(bar_ifull + 8 * e, eph);
                 int idx0[8], idx1[8];
+                const bool ok0 = first_tap(blk) + sub < k3;
+                const bool ok1 = blk + 1 < total_blocks && first_tap(blk + 1) + sub < k3; // odd block count: zero dummy
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint32_t entry = smem_idx + e * 1024 + (my_row + 4 * i) * 4;
+                    const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * 512 + (my_row + 4 * i) * 4;
                     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx0[i]) : "r"(entry) : "memory");
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1[i]) : "r"(entry + 512) : "memory");
-                    if (4 * i >= rows_left)
-                        idx0[i] = idx1[i] = -1;
-                }
-                if (blk + 1 >= total_blocks) { // odd block count: the last unit's second block is a zero dummy
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1[i]) : "r"(entry + G * 512) : "memory");
+                    if (4 * i >= rows_left || !ok0)
+                        idx0[i] = -1;
+                    if (4 * i >= rows_left || !ok1)
                         idx1[i] = -1;
                 }
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                 const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
-                gather_rows(stage, swz0, swz1, xq + (blk % CB) * 64, CIN, idx0);
-                gather_rows(stage + WG_BLOCK_BYTES, swz0, swz1, xq + ((blk + 1) % CB) * 64, CIN, idx1);
+                gather_rows(stage, swz0, swz1, xq + (CIN >= 64 ? (blk % CB) * 64 : 0), CIN, idx0);
+                gather_rows(stage + WG_BLOCK_BYTES, swz0, swz1, xq + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), CIN, idx1);
                 __syncwarp();
                 if (lane == 0)
                     mbar_arrive(bar_iempty + 8 * e);
@@ -175,7 +188,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     s = 0;
                     ph ^= 1u;
                 }
-                if (++e == WG_IDX_RING) {
+                if (++e == RING) {
                     e = 0;
                     eph ^= 1u;
                 }
@@ -183,22 +196,28 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         }
         cp_async_wait_all();
 
-        // ================= epilogue: accumulators -> fp32 partial slice =================
+        // ================= epilogue: accumulators -> fp32 partial slice [k][ci][co] =================
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started);
-        const int half = warp >> 1;                   // which A block of the unit this warp's TMEM lanes belong to
-        const int ci_local = (warp & 1) * 32 + lane;  // channel inside the block
+        const int half = warp >> 1;                  // which A block of the unit this warp's TMEM lanes belong to
+        const int kk = (warp & 1) * 32 + lane;       // reduction-side element inside the block
         float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
+        constexpr int EC = COUT >= 32 ? 32 : 16;     // columns drained per tcgen05.ld
         for (int ul = 0; ul < nunits; ++ul) {
             const int blk = 2 * (unit0 + ul) + half;
-            const bool live = blk < total_blocks;
-            const int tap = blk / CB, ci = (blk % CB) * 64 + ci_local;
+            const int tap = CIN >= 64 ? blk / CB : blk * G + kk / CIN;
+            const int ci = CIN >= 64 ? (blk % CB) * 64 + kk : kk % CIN;
+            const bool live = blk < total_blocks && tap < k3;
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
+            for (int c0 = 0; c0 < COUT; c0 += EC) {
                 uint32_t acc[32];
                 if ((started >> ul) & 1u) {
-                    tmem_ld_32x32b_x32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * COUT + c0), acc);
+                    const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * NPAD + c0);
+                    if (EC == 32)
+                        tmem_ld_32x32b_x32(taddr, acc);
+                    else
+                        tmem_ld_32x32b_x16(taddr, acc);
                     tmem_ld_wait();
                 } else { // no row of this CTA's tiles ever reached these taps
 #pragma unroll
@@ -208,7 +227,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 if (live) {
                     uint4 *dst = reinterpret_cast<uint4 *>(slice + (int64_t(tap) * CIN + ci) * COUT + c0);
 #pragma unroll
-                    for (int v = 0; v < 8; ++v)
+                    for (int v = 0; v < EC / 4; ++v)
                         dst[v] = make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
                 }
             }
@@ -216,7 +235,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     } else if (warp == WG_WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // MN-major SWIZZLE_128B descriptors: LBO = distance between the two 64-channel blocks, SBO = 8-row group
+            // MN-major SWIZZLE_128B descriptors: LBO = distance between the two 64-wide blocks, SBO = 8-row group
             const uint64_t desc_hi = make_smem_desc_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFF00000000ull;
             const uint32_t lbo = uint32_t(WG_BLOCK_BYTES >> 4) << 16;
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | lbo;
@@ -235,7 +254,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     const uint32_t acc0 = (started >> ul) & 1u;
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) // 16 rows (K) per MMA = two 8-row swizzle groups = 2048 B = 128 units
-                        umma_f16(tmem_base + uint32_t(ul * COUT), desc_hi | (a_lo + 128 * kk), desc_hi | (b_lo + 128 * kk), idesc,
+                        umma_f16(tmem_base + uint32_t(ul * NPAD), desc_hi | (a_lo + 128 * kk), desc_hi | (b_lo + 128 * kk), idesc,
                                  acc0 | uint32_t(kk != 0));
                     umma_commit(bar_empty + 8 * s);
                     started |= 1u << ul;
@@ -252,7 +271,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         }
         __syncwarp();
     } else {
-        // ================= kernel-map streamer (whole warp): both taps of every live unit, 2 x 512 B =================
+        // ================= kernel-map streamer (whole warp): every tap of both blocks of each live unit =================
         int e = 0;
         uint32_t eph = 0;
         const int32_t *lane_nbr = nbr + lane * 4;
@@ -260,12 +279,18 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             const uint32_t live = live_units(tile);
             for (uint32_t rest = live; rest; rest &= rest - 1u) {
                 const int blk = 2 * (unit0 + __ffs(rest) - 1);
-                const int ta = blk / CB, tb_ = (blk + 1 < total_blocks ? blk + 1 : blk) / CB;
                 mbar_wait(bar_iempty + 8 * e, eph ^ 1u);
-                cp_async16(smem_idx + e * 1024 + lane * 16, lane_nbr + int64_t(ta) * pitch + tile * WG_TILE, 16u);
-                cp_async16(smem_idx + e * 1024 + 512 + lane * 16, lane_nbr + int64_t(tb_) * pitch + tile * WG_TILE, 16u);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int sb = 0; sb < G; ++sb) {
+                        const int tap = first_tap(blk + h) + sb;
+                        if (blk + h < total_blocks && tap < k3)
+                            cp_async16(smem_idx + e * Cfg::RING_BYTES + (h * G + sb) * 512 + lane * 16,
+                                       lane_nbr + int64_t(tap) * pitch + tile * WG_TILE, 16u);
+                    }
                 cp_async_arrive_noinc(bar_ifull + 8 * e);
-                if (++e == WG_IDX_RING) {
+                if (++e == RING) {
                     e = 0;
                     eph ^= 1u;
                 }
@@ -286,8 +311,9 @@ struct WgradPlan {
 
 static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3) {
     WgradPlan p;
-    const int total_units = (k3 * (cin / 64) + 1) / 2;
-    const int max_units = 512 / cout;
+    const int total_blocks = cin >= 64 ? k3 * (cin / 64) : int(ceil_div(k3, 64 / cin));
+    const int total_units = (total_blocks + 1) / 2;
+    const int max_units = 512 / (cout >= 64 ? cout : 64);
     p.groups = int(ceil_div(total_units, max_units));
     p.units_per_group = int(ceil_div(total_units, p.groups)); // balanced groups
     const int64_t tiles = ceil_div(n_out, WG_TILE);
@@ -310,7 +336,7 @@ template <int CIN, int COUT, int STAGES> static int launch_tc_wgrad(const WgradA
         configured = true;
     }
     const WgradPlan p = plan_wgrad(a.n_out, CIN, COUT, a.k3);
-    const uint32_t idesc = make_idesc_f16(128, COUT, a.dtype == FVC_BF16, true, true);
+    const uint32_t idesc = make_idesc_f16(128, Cfg::NPAD, a.dtype == FVC_BF16, true, true);
     float *partial = reinterpret_cast<float *>(a.scratch);
     dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
     kernel<<<grid, WG_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), reinterpret_cast<const uint16_t *>(a.dy),
@@ -325,8 +351,8 @@ bool tc_wgrad_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
         return false;
     if (k3 < 1 || k3 > 4096)
         return false;
-    const bool ok = (cin == 64 || cin == 128 || cin == 256) && (cout == 64 || cout == 128 || cout == 256);
-    return ok;
+    auto pow2 = [](int c) { return c == 16 || c == 32 || c == 64 || c == 128 || c == 256; };
+    return pow2(cin) && pow2(cout);
 }
 
 size_t tc_wgrad_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t) {
@@ -346,15 +372,18 @@ int tc_wgrad(const WgradArgs &a) {
 #define FVC_WG_CASE(CI, CO, S)       \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S>(a);
-    FVC_WG_CASE(64, 64, 4)
-    FVC_WG_CASE(64, 128, 4)
-    FVC_WG_CASE(64, 256, 2)
-    FVC_WG_CASE(128, 64, 4)
-    FVC_WG_CASE(128, 128, 4)
-    FVC_WG_CASE(128, 256, 2)
-    FVC_WG_CASE(256, 64, 4)
-    FVC_WG_CASE(256, 128, 4)
-    FVC_WG_CASE(256, 256, 2)
+#define FVC_WG_CIN(CI)       \
+    FVC_WG_CASE(CI, 16, 4)   \
+    FVC_WG_CASE(CI, 32, 4)   \
+    FVC_WG_CASE(CI, 64, 4)   \
+    FVC_WG_CASE(CI, 128, 4)  \
+    FVC_WG_CASE(CI, 256, 2)
+    FVC_WG_CIN(16)
+    FVC_WG_CIN(32)
+    FVC_WG_CIN(64)
+    FVC_WG_CIN(128)
+    FVC_WG_CIN(256)
+#undef FVC_WG_CIN
 #undef FVC_WG_CASE
     return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core wgrad kernel for channels %d -> %d", a.cin, a.cout);
 }

@@ -275,21 +275,23 @@ def _matmul_weight_matrix(weights: torch.Tensor) -> torch.Tensor:
 
 
 class _GatherScatterConvFn(torch.autograd.Function):
-    """autograd glue over gs_conv / gs_conv_backward (either direction)."""
+    """autograd glue over gs_conv / gs_conv_backward (either direction); an optional bias is added in the kernel epilogue."""
 
     @staticmethod
-    def forward(ctx, features, weights, topo, transposed):  # type: ignore[override]
+    def forward(ctx, features, weights, bias, topo, transposed):  # type: ignore[override]
         fn = _fvdb_cpp.gs_conv_transpose if transposed else _fvdb_cpp.gs_conv
         ctx.save_for_backward(features, weights)
-        ctx.topo, ctx.transposed = topo, transposed
-        return fn(features, weights, topo)
+        ctx.topo, ctx.transposed, ctx.has_bias = topo, transposed, bias is not None
+        return fn(features, weights, topo, bias)
 
     @staticmethod
     def backward(ctx, grad_output):  # type: ignore[override]
         features, weights = ctx.saved_tensors
         fn = _fvdb_cpp.gs_conv_transpose_backward if ctx.transposed else _fvdb_cpp.gs_conv_backward
-        grad_features, grad_weights = fn(grad_output.contiguous(), features, weights, ctx.topo)
-        return grad_features, grad_weights, None, None
+        grad_output = grad_output.contiguous()
+        grad_features, grad_weights = fn(grad_output, features, weights, ctx.topo)
+        grad_bias = grad_output.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return grad_features, grad_weights, grad_bias, None, None
 
 
 class _CoverageReportCache:
@@ -438,9 +440,7 @@ class ConvolutionPlan:
         topology = _backend_topology(backend)
         if topology is None:
             raise TypeError(f"Unknown backend type: {type(backend)}")
-        out = _GatherScatterConvFn.apply(features, weights, topology, self._transposed)
-        if bias is not None:
-            out = out + bias
+        out = _GatherScatterConvFn.apply(features, weights, bias, topology, self._transposed)
         return out if is_flat else self._target_grid.jagged_like(out)
 
     # ---- properties -----------------------------------------------------------------------

@@ -185,6 +185,9 @@ _VALUE_CASES = [
     (torch.bfloat16, 128, 128, 3, 1, 2e-2), (torch.bfloat16, 64, 128, 2, 2, 2e-2), (torch.bfloat16, 256, 256, 3, 1, 2e-2),
     (torch.bfloat16, 64, 32, 3, 2, 2e-2), (torch.float16, 64, 64, 3, 1, 2e-2), (torch.float16, 32, 64, 3, 1, 2e-2),
     (torch.bfloat16, 24, 40, 3, 1, 2e-2),
+    # packed small-channel tensor-core path: Cin < 64 puts 64 / Cin taps in one reduction block
+    (torch.bfloat16, 16, 32, 3, 1, 2e-2), (torch.bfloat16, 32, 16, 2, 2, 2e-2), (torch.bfloat16, 16, 64, (3, 5, 1), (1, 2, 1), 2e-2),
+    (torch.float16, 16, 16, 3, 1, 2e-2), (torch.bfloat16, 128, 16, 3, 1, 2e-2), (torch.bfloat16, 32, 256, 3, 1, 2e-2),
 ]
 
 
@@ -353,11 +356,22 @@ def test_nn_modules_train_step(fvdb):
         assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
     with pytest.raises(ValueError, match="mismatched"):
         conv(x, down)
+    # fused bias == separate bias add (reference modules.py:370-371), forward and gradient, on both kernel families
+    for module, dtype in ((conv, torch.float32), (fvdb.nn.SparseConv3d(64, 64, 3).to(DEV).bfloat16(), torch.bfloat16)):
+        xin = source.jagged_like(torch.randn(source.total_voxels, module.in_channels, device=DEV).to(dtype))
+        module.zero_grad()
+        fused = module(xin, same).jdata
+        fused.float().square().mean().backward()
+        fused_grad = module.bias.grad.clone()
+        plain = same.execute(xin, module.weight).jdata.float() + module.bias.float()
+        torch.testing.assert_close(fused.float(), plain, rtol=2e-2 if dtype == torch.bfloat16 else 1e-5, atol=2e-2 if dtype == torch.bfloat16 else 1e-5)
+        want_grad = torch.autograd.grad(plain.square().mean(), module.bias)[0].float()
+        torch.testing.assert_close(fused_grad.float(), want_grad, rtol=5e-2, atol=1e-3)
     # strided (non-contiguous) nn weights give the same result as a contiguous copy
     torch.testing.assert_close(same.execute(x, conv.weight).jdata, same.execute(x, conv.weight.detach().contiguous()).jdata)
 
 
-@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 32), (256, 64)])
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 32), (256, 64), (32, 32), (16, 16), (16, 128)])
 def test_tensor_core_identity_map_is_plain_gemm(fvdb, cin, cout):
     # K^3 = 1 on two equal-looking but distinct grids: the kernel map is the identity, so the tcgen05 kernel
     # must reproduce x @ W^T -- isolates UMMA descriptors / swizzle / TMEM epilogue from the gather logic.
