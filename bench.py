@@ -38,6 +38,8 @@ CONFIGS = {
     # name: (generator, grids, target voxels per grid, kernel, cin, cout, dtype)
     "c1": dict(gen="sphere_shell", grids=1, voxels=100_000, kernel=3, cin=32, cout=32, dtype="f32", desc="C1 single grid ~100k voxels, 3^3 32->32 fp32"),
     "c2": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=64, cout=64, dtype="bf16", desc="C2 ScanNet-shaped 8 grids x ~200k voxels, 3^3 64->64 bf16 fwd+bwd"),
+    "c3": dict(gen="indoor_room", grids=16, voxels=150_000, kernel=3, cin=32, cout=32, dtype="bf16", desc="C3 sparse UNet block stack (3^3 convs, 2^3 s2 down, transposed up, 32..256 ch) on 16 indoor grids, training step"),
+    "c2x128": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C2-shaped 8 grids x ~200k voxels, 3^3 128->128 bf16 fwd+bwd"),
     "c4": dict(gen="lidar_sweep", grids=32, voxels=1_000_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C4 KITTI-shaped 32 grids x ~1M voxels, 3^3 128->128 bf16"),
     "c5": dict(gen="random_occupancy", grids=8, voxels=4_979_000, kernel=5, cin=16, cout=16, dtype="bf16", desc="C5 8 grids x ~5M voxels, 5^3 16->16"),
 }
@@ -351,6 +353,134 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# C3: sparse UNet block stack training step (strided down-convs, exact-transpose up-convs, wgrad all-reduce)
+# ------------------------------------------------------------------------------------------------------
+
+
+def run_unet(args, cfg):
+    import torch.distributed as dist
+
+    import fvdb
+    from fvdb.distributed import allreduce_gradients
+    from fvdb._lib import launch_count
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = DTYPES[cfg["dtype"]]
+    grids_here = cfg["grids"] // world if world <= cfg["grids"] else 1  # the batch is partitioned BY GRID (strong scaling)
+    coords = make_coords({**cfg, "grids": grids_here}, rank, dev)
+    g0 = fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(coords))
+    widths = [32, 64, 128, 256]
+    Plan = fvdb.ConvolutionPlan
+    grids, same, down = [g0], [], []
+    for level in range(4):
+        same.append(Plan.from_grid_batch(3, 1, grids[level], grids[level]))
+        if level < 3:
+            down.append(Plan.from_grid_batch(2, 2, grids[level]))
+            grids.append(down[-1].target_grid_batch)
+    up = [Plan.from_plan_transposed(p) for p in down]  # exact adjoint topology of the matching down-conv
+
+    class Block(torch.nn.Module):
+        def __init__(self, conv, channels):
+            super().__init__()
+            self.conv, self.norm = conv, torch.nn.BatchNorm1d(channels)
+
+        def forward(self, x, plan):
+            y = self.conv(x, plan)
+            return y.jagged_like(torch.relu(self.norm(y.jdata)))
+
+    class Stack(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            nn = fvdb.nn
+            self.enc = torch.nn.ModuleList([torch.nn.ModuleList([Block(nn.SparseConv3d(c, c, 3), c) for _ in range(2)]) for c in widths])
+            self.down = torch.nn.ModuleList([Block(nn.SparseConv3d(widths[i], widths[i + 1], 2, 2), widths[i + 1]) for i in range(3)])
+            self.up = torch.nn.ModuleList([Block(nn.SparseConvTranspose3d(widths[i + 1], widths[i], 2, 2), widths[i]) for i in range(3)])
+            self.dec = torch.nn.ModuleList([torch.nn.ModuleList([Block(nn.SparseConv3d(c, c, 3), c) for _ in range(2)]) for c in widths[:3]])
+
+        def forward(self, x):
+            skips = []
+            for level in range(4):
+                for blk in self.enc[level]:
+                    x = blk(x, same[level])
+                if level < 3:
+                    skips.append(x)
+                    x = self.down[level](x, down[level])
+            for level in (2, 1, 0):
+                x = self.up[level](x, up[level])
+                x = x.jagged_like(x.jdata + skips[level].jdata)
+                for blk in self.dec[level]:
+                    x = blk(x, same[level])
+            return x
+
+    torch.manual_seed(1234)  # identical replicas on every rank
+    model = Stack().to(dev).to(dtype)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(1 + rank)
+    n = g0.total_voxels
+    x_host = torch.randn((n, 32), generator=gen).to(dtype).pin_memory()
+    feats = g0.jagged_like(x_host.to(dev))
+    collectives = 0
+
+    def step():
+        nonlocal collectives
+        opt.zero_grad(set_to_none=True)
+        out = model(feats)
+        loss = out.jdata.float().square().mean()
+        loss.backward()
+        collectives = allreduce_gradients(model.parameters()) if world > 1 else 0
+        opt.step()
+        return loss
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = launch_count()
+    with ClockSampler(local_rank) as clocks:
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(args.steps):
+            loss = step()
+        b.record()
+        barrier()
+    launches = launch_count() - l0
+    ms = a.elapsed_time(b) / args.steps
+    stats = torch.tensor([ms, float(n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx, sm = stats.clone(), stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, total_n = float(mx[0]), float(sm[1])
+    else:
+        total_n = float(n)
+    if rank == 0:
+        pairs = {f"L{lv}": int(same[lv]._backend.topology.total_pairs) for lv in range(4)}
+        line = {
+            "metric": "sparse-conv voxels/sec fwd+bwd", "value": total_n / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": cfg["desc"], "grids_per_gpu": grids_here, "voxels_per_gpu": n, "voxels_per_level": [g.total_voxels for g in grids],
+                       "pairs_3x3x3_per_level": pairs, "layers": "2x[3^3 c->c] per level, 2^3 s2 down 32-64-128-256, exact-transpose up, BN+ReLU in torch, SGD step",
+                       "collective": f"{collectives} bucketed all_reduce(grad) calls per step" if world > 1 else "none"},
+            "loss": float(loss), "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None, "e2e": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -359,10 +489,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grids", type=int, default=0, help="override the number of grids per GPU (experiments)")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.grids:
+        cfg["grids"] = args.grids
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.config == "c3":
+        run_unet(args, cfg)
     else:
         run_ours(args, cfg)
 
