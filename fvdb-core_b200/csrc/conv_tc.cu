@@ -432,6 +432,16 @@ int tc_forward(const ConvArgs &a) {
         default: break;
         }
     }
+    if (a.cin == 128 && a.cout == 128) {
+        const char *v = getenv("FVC_TC_VARIANT");
+        switch (v ? atoi(v) : 0) {
+        case 1: return launch_tc_fwd<128, 128, 2, 3, 2, 4>(a, img);
+        case 2: return launch_tc_fwd<128, 128, 4, 6, 4, 4>(a, img);
+        case 3: return launch_tc_fwd<128, 128, 4, 8, 3, 8>(a, img);
+        case 4: return launch_tc_fwd<128, 128, 2, 4, 2, 4>(a, img);
+        default: break;
+        }
+    }
 #define FVC_TC_CASE(CI, CO, T, S, B) \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_fwd<CI, CO, T, S, B, 4>(a, img);
@@ -439,7 +449,7 @@ int tc_forward(const ConvArgs &a) {
     FVC_TC_CASE(CI, 16, 8, 4, 3)  \
     FVC_TC_CASE(CI, 32, 8, 4, 3)  \
     FVC_TC_CASE(CI, 64, 4, 4, 3)  \
-    FVC_TC_CASE(CI, 128, 4, 8, 3) \
+    FVC_TC_CASE(CI, 128, 2, 3, 2) \
     FVC_TC_CASE(CI, 256, 2, 6, 3)
     FVC_TC_CIN(16)
     FVC_TC_CIN(32)
