@@ -94,21 +94,29 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     // the same live-unit bitmask from the tile's tap bitmask (K^3 <= 128; larger kernels do not skip).
     const int words = (k3 + 63) >> 6;
     const bool use_mask = tile_mask != nullptr && words <= 2;
+    __shared__ unsigned long long s_unit_taps[8][2]; // taps (bits of the two mask words) that belong to each unit
+    if (threadIdx.x < 8) {
+        unsigned long long lo = 0ull, hi = 0ull;
+        const int ul = threadIdx.x;
+        if (ul < nunits) {
+            const int blk = 2 * (unit0 + ul);
+            const int t_lo = first_tap(blk);
+            int t_hi = first_tap(blk + 1 < total_blocks ? blk + 1 : blk) + G; // exclusive
+            t_hi = t_hi < k3 ? t_hi : k3;
+            for (int tap = t_lo; tap < t_hi && tap < 128; ++tap)
+                (tap < 64 ? lo : hi) |= 1ull << (tap & 63);
+        }
+        s_unit_taps[ul][0] = lo;
+        s_unit_taps[ul][1] = hi;
+    }
     auto live_units = [&](int64_t tile) -> uint32_t {
         if (!use_mask)
             return (1u << nunits) - 1u;
         const unsigned long long m0 = __ldg(tile_mask + tile * words), m1 = words > 1 ? __ldg(tile_mask + tile * words + 1) : 0ull;
         uint32_t live = 0;
-        for (int ul = 0; ul < nunits; ++ul) {
-            const int blk = 2 * (unit0 + ul);
-            const int t_lo = first_tap(blk);
-            int t_hi = first_tap(blk + 1 < total_blocks ? blk + 1 : blk) + G; // exclusive
-            t_hi = t_hi < k3 ? t_hi : k3;
-            unsigned long long any = 0ull;
-            for (int tap = t_lo; tap < t_hi; ++tap)
-                any |= ((tap < 64 ? m0 : m1) >> (tap & 63)) & 1ull;
-            live |= uint32_t(any) << ul;
-        }
+#pragma unroll
+        for (int ul = 0; ul < 8; ++ul)
+            live |= uint32_t(((m0 & s_unit_taps[ul][0]) | (m1 & s_unit_taps[ul][1])) != 0ull) << ul;
         return live;
     };
 
