@@ -46,6 +46,11 @@ CONFIGS = {
 DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16, "f64": torch.float64}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same command
+# (profiles/r01_ncu_full_v5_summary.txt); only known for the default workload.
+NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 171.2e6, "dgrad": 297.7e6 + 171.2e6, "wgrad": 565.9e6 + 7.5e6}}
+
+
 def load_peaks() -> dict:
     path = REPO / "MEASURED_PEAKS.json"
     if path.exists():
@@ -331,7 +336,9 @@ def run_ours(args, cfg):
             cpu = {"value": vox / sec, "unit": "voxels/s", "cores": threads, "kind": "port",
                    "sample": f"1 of {cfg['grids']} grids ({vox} voxels, {pairs} pairs) fwd+bwd fp32, median of 2 after 1 warm-up; oracle port of the GatherScatterDefault CPU path"}
         roof = dict(per_kernel[dominant])
-        roof.update({"kernel": dominant, "traffic": None, "peak_source": peaks["source"]})
+        traffic = NCU_TRAFFIC_BYTES.get(args.config, {}).get(dominant) if cfg["grids"] == CONFIGS[args.config]["grids"] else None
+        roof.update({"kernel": dominant, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_ncu_full_v5_summary.txt" if traffic else None,
+                     "peak_source": peaks["source"]})
         line = {
             "metric": "sparse-conv voxels/sec fwd+bwd", "value": total_n / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],

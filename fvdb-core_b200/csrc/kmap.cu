@@ -107,52 +107,68 @@ kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transpose
     }
     __syncthreads();
 
-    // (4) all voxel x tap probes; j (voxel) is the fastest index so stores to nbr[k][base + j] coalesce
-    const uint32_t items = uint32_t(cnt) * uint32_t(k3);
-    for (uint32_t item = tid; item < items; item += KM_THREADS) {
-        const int k = int(item / uint32_t(cnt)), j = int(item - uint32_t(k) * uint32_t(cnt));
-        const int n = s_vox[j];
-        const int c[3] = {origin[0] + (n >> 6), origin[1] + ((n >> 3) & 7), origin[2] + (n & 7)};
-        int t[3];
-        if (small_taps) {
-            const uint32_t packed = s_tap[k];
-            t[0] = int(packed >> 20), t[1] = int((packed >> 10) & 1023), t[2] = int(packed & 1023);
-        } else {
-            t[0] = k / k12, t[1] = (k / g.k[2]) % g.k[1], t[2] = k % g.k[2];
-        }
-        int p[3];
-        bool ok = true;
-        if (!transposed) {
+    // (4) all voxel x tap probes.  A lane keeps one voxel's coordinates in registers and walks the taps its warp owns
+    //     (k = warp, warp + 4, ...): no per-probe division, stores to nbr[k][base + j] coalesce across the lanes,
+    //     and per-tap pair counts come from one ballot per (warp, tap) instead of one atomic per pair.
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool unit_stride = g.s[0] == 1 && g.s[1] == 1 && g.s[2] == 1;
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+        const int j = j0 + lane;
+        const bool has = j < cnt;
+        const int n = has ? s_vox[j] : 0;
+        // forward: S * c - pad (then + tap);  transposed: c + pad (then - tap, then / S)
+        int c[3] = {origin[0] + (n >> 6), origin[1] + ((n >> 3) & 7), origin[2] + (n & 7)};
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
-                p[d] = g.s[d] * c[d] + t[d] - g.pad[d]; // fineFromCoarse
-        } else {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) { // coarseFromFine with the divisibility test
-                const int numer = c[d] - t[d] + g.pad[d];
-                ok = ok && floor_mod(numer, g.s[d]) == 0;
-                p[d] = floor_div(numer, g.s[d]);
-            }
-        }
-        int val = -1;
-        if (ok) {
-            if (cached) {
-                const int li = (((p[0] >> 3) - box.lmin[0]) * box.n[1] + ((p[1] >> 3) - box.lmin[1])) * box.n[2] +
-                               ((p[2] >> 3) - box.lmin[2]);
-                if (s_leaf[li] >= 0) {
-                    const int w = p[0] & 7;
-                    val = leaf_value(s_mask[li][w], s_prefix[li][w], s_base[li], p[1], p[2]);
-                }
+        for (int d = 0; d < 3; ++d)
+            c[d] = transposed ? c[d] + g.pad[d] : g.s[d] * c[d] - g.pad[d];
+        for (int k = warp; k < k3; k += KM_THREADS / 32) {
+            int t[3];
+            if (small_taps) {
+                const uint32_t packed = s_tap[k];
+                t[0] = int(packed >> 20), t[1] = int((packed >> 10) & 1023), t[2] = int(packed & 1023);
             } else {
-                val = lookup_row(feat, b, p[0], p[1], p[2]);
+                t[0] = k / k12, t[1] = (k / g.k[2]) % g.k[1], t[2] = k % g.k[2];
             }
-        }
-        nbr[int64_t(k) * pitch + base + j] = val;
-        if (val >= 0) {
-            if (small_taps)
-                atomicAdd(&s_cnt[k], 1u);
-            else
-                atomicAdd(tap_counts + k, 1ull);
+            int p[3];
+            bool ok = has;
+            if (!transposed) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    p[d] = c[d] + t[d]; // fineFromCoarse
+            } else if (unit_stride) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    p[d] = c[d] - t[d];
+            } else {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { // coarseFromFine with the divisibility test
+                    const int numer = c[d] - t[d];
+                    ok = ok && floor_mod(numer, g.s[d]) == 0;
+                    p[d] = floor_div(numer, g.s[d]);
+                }
+            }
+            int val = -1;
+            if (ok) {
+                if (cached) {
+                    const int li = (((p[0] >> 3) - box.lmin[0]) * box.n[1] + ((p[1] >> 3) - box.lmin[1])) * box.n[2] +
+                                   ((p[2] >> 3) - box.lmin[2]);
+                    if (s_leaf[li] >= 0) {
+                        const int w = p[0] & 7;
+                        val = leaf_value(s_mask[li][w], s_prefix[li][w], s_base[li], p[1], p[2]);
+                    }
+                } else {
+                    val = lookup_row(feat, b, p[0], p[1], p[2]);
+                }
+            }
+            if (has)
+                nbr[int64_t(k) * pitch + base + j] = val;
+            const unsigned hits = __ballot_sync(0xffffffffu, val >= 0);
+            if (lane == 0 && hits) {
+                if (small_taps)
+                    s_cnt[k] += __popc(hits); // tap k belongs to this warp alone
+                else
+                    atomicAdd(tap_counts + k, (unsigned long long)__popc(hits));
+            }
         }
     }
     if (small_taps) {

@@ -391,3 +391,30 @@ def test_tensor_core_identity_map_is_plain_gemm(fvdb, cin, cout):
     want = x.float() @ w[:, :, 0, 0, 0].float().T
     assert _rel_err(y, want.cpu()) <= 1e-2
     torch.testing.assert_close(y.float(), want, rtol=2e-2, atol=2e-2)
+
+
+def test_pred_gather_igemm_backend_admission_and_values(fvdb):
+    # reference: backend='pred_gather_igemm' (forward-only SM80 TF32 kernel, tests/unit/test_conv_pred_gather_igemm.py);
+    # here the same engine serves it: admission rules kept, values equal the default backend's, backward works.
+    coords = _random_batch(13, n=5000, extent=14, batches=1, dup=False)[0]
+    grid = _grid(fvdb, [coords])
+    igemm = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid, grid, expert_config={"backend": "pred_gather_igemm"}, channel_pairs=((64, 64),))
+    default = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid, grid)
+    assert type(igemm._backend).__name__ == "_PredGatherIGemmBackend" and igemm.valid_usage(64, 64, 3, 1, False) and not igemm.valid_usage(48, 64, 3, 1, False)
+    gen = torch.Generator().manual_seed(8888)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        x = torch.randn((grid.total_voxels, 64), generator=gen).to(dtype).to(DEV).requires_grad_()
+        w = (torch.randn((64, 64, 3, 3, 3), generator=gen) / 41.0).to(dtype).to(DEV).requires_grad_()
+        y = igemm.execute(x, w)
+        torch.testing.assert_close(y, default.execute(x, w), rtol=0, atol=0)  # same kernels, deterministic
+        want = _oracle_run(default._backend.topology, x.detach(), w.detach(), torch.ones_like(y))[0]
+        assert _rel_err(y.detach(), want) <= tol
+        gx, gw = torch.autograd.grad(y.float().sum(), (x, w))
+        assert torch.isfinite(gx).all() and torch.isfinite(gw).all()
+    direct = fvdb._fvdb_cpp.pred_gather_igemm_conv(x.detach(), w.detach(), grid.data, grid.data, 3, 1)
+    torch.testing.assert_close(direct, default.execute(x.detach(), w.detach()), rtol=0, atol=0)
+    any_pairs = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid, grid, expert_config={"backend": "pred_gather_igemm"})
+    with pytest.raises(ValueError, match="channel counts divisible by 32"):
+        any_pairs.execute(torch.ones(grid.total_voxels, 48, device=DEV), torch.ones(64, 48, 3, 3, 3, device=DEV))
+    with pytest.raises(ValueError, match="only batch size 1"):
+        fvdb.ConvolutionPlan.from_grid_batch(3, 1, _grid(fvdb, [coords, coords]), expert_config={"backend": "pred_gather_igemm"})
