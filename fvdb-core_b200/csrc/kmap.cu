@@ -1,7 +1,7 @@
 // kmap.cu -- kernel-map construction, CSR view, lookups and target-topology candidate emission.
 //
 // Replaces GatherScatterDefault.cu:92-294 (two full sweeps with one un-cached root-to-leaf walk per
-// (voxel, tap) probe and K^3 contended global counters).  Here one CTA owns one *output leaf*: its
+// (voxel, tap) probe and K^3 contended global counters).  Here one warp owns one *output leaf*: its
 // lanes walk the tree once per source leaf of the probe neighbourhood (<= 3x3x3 leaves for every
 // K <= 9 stride-1 kernel), stage those leaves' mask / prefix / base lines in shared memory with
 // 16-byte loads, and answer all voxel x tap probes from shared memory.  The map is written tap-major
@@ -12,8 +12,9 @@
 
 namespace fvc {
 
-constexpr int KM_THREADS = 128;
-constexpr int KM_MAX_NB = 128;    // cached source leaves per output leaf
+constexpr int KM_WARPS = 4;       // output leaves per CTA: one warp owns one leaf
+constexpr int KM_THREADS = KM_WARPS * 32;
+constexpr int KM_MAX_NB = 64;     // cached source leaves per output leaf (3x3x3 = 27 covers every K <= 9 stride-1 kernel)
 constexpr int KM_MAX_TAPS = 1024; // taps with shared-memory tap table / counters
 
 struct LeafBox {
@@ -45,129 +46,135 @@ __device__ __forceinline__ LeafBox probe_box(const Geometry &g, const int origin
     return box;
 }
 
+// One WARP per output leaf (four leaves per CTA keep four independent latency chains in flight per CTA: ncu showed
+// the one-CTA-per-leaf version waiting at block barriers behind 27 serial tree walks).  The warp's lanes walk the
+// tree once per source leaf of the probe box, stage those leaves' mask / prefix / base lines in shared memory with
+// 16-byte loads, then every lane keeps one output voxel in registers and answers its K^3 probes from shared memory.
 __global__ void __launch_bounds__(KM_THREADS)
 kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transposed, int32_t *__restrict__ nbr,
                   int64_t pitch, unsigned long long *__restrict__ tap_counts) {
-    __shared__ __align__(16) uint64_t s_mask[KM_MAX_NB][8];
-    __shared__ __align__(16) uint16_t s_prefix[KM_MAX_NB][8];
-    __shared__ int s_base[KM_MAX_NB];
-    __shared__ int s_leaf[KM_MAX_NB];
-    __shared__ uint16_t s_vox[512];
+    __shared__ __align__(16) uint64_t s_mask[KM_WARPS][KM_MAX_NB][8];
+    __shared__ __align__(16) uint16_t s_prefix[KM_WARPS][KM_MAX_NB][8];
+    __shared__ int s_base[KM_WARPS][KM_MAX_NB];
+    __shared__ int s_leaf[KM_WARPS][KM_MAX_NB];
+    __shared__ uint16_t s_vox[KM_WARPS][512];
     __shared__ uint32_t s_tap[KM_MAX_TAPS];
     __shared__ uint32_t s_cnt[KM_MAX_TAPS];
 
-    const int tid = threadIdx.x;
-    const FvcLeaf *L = out.leaves + blockIdx.x;
-    const int b = __ldg(&L->batch);
-    const int origin[3] = {__ldg(&L->origin[0]), __ldg(&L->origin[1]), __ldg(&L->origin[2])};
-    const int base = __ldg(&L->base);
-    const int cnt = __ldg(&L->count);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k3 = int(g.volume);
     const bool small_taps = k3 <= KM_MAX_TAPS;
     const int k12 = g.k[1] * g.k[2];
-
-    const LeafBox box = probe_box(g, origin, transposed);
-    const bool cached = box.total <= KM_MAX_NB;
-
-    // (1) lanes walk the tree in parallel, one source leaf each
-    if (cached) {
-        for (int t = tid; t < box.total; t += KM_THREADS) {
-            const int c = t % box.n[2], bb = (t / box.n[2]) % box.n[1], a = t / (box.n[2] * box.n[1]);
-            const int leaf = find_leaf(feat, b, (box.lmin[0] + a) << 3, (box.lmin[1] + bb) << 3, (box.lmin[2] + c) << 3);
-            s_leaf[t] = leaf;
-            s_base[t] = leaf >= 0 ? __ldg(&feat.leaves[leaf].base) : 0;
-        }
-    }
     if (small_taps) {
         for (int k = tid; k < k3; k += KM_THREADS) {
             s_tap[k] = (uint32_t(k / k12) << 20) | (uint32_t((k / g.k[2]) % g.k[1]) << 10) | uint32_t(k % g.k[2]);
             s_cnt[k] = 0;
         }
     }
-    // (2) compact the output leaf's active voxels: rank inside the leaf == row - base
-    for (int n = tid; n < 512; n += KM_THREADS) {
-        const int w = n >> 6, bit = n & 63;
-        const uint64_t m = __ldg(L->mask + w);
-        if ((m >> bit) & 1ull)
-            s_vox[int(__ldg(L->prefix + w)) + __popcll(m & ((1ull << bit) - 1ull))] = uint16_t(n);
-    }
-    __syncthreads();
-    // (3) stage mask (4 x 16 B) + prefix (1 x 16 B) of every source leaf
-    if (cached) {
-        for (int e = tid; e < box.total * 5; e += KM_THREADS) {
-            const int li = e / 5, part = e % 5, leaf = s_leaf[li];
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (leaf >= 0)
-                v = __ldg(reinterpret_cast<const uint4 *>(feat.leaves + leaf) + part);
-            if (part < 4)
-                reinterpret_cast<uint4 *>(&s_mask[li][0])[part] = v;
-            else
-                *reinterpret_cast<uint4 *>(&s_prefix[li][0]) = v;
-        }
-    }
     __syncthreads();
 
-    // (4) all voxel x tap probes.  A lane keeps one voxel's coordinates in registers and walks the taps its warp owns
-    //     (k = warp, warp + 4, ...): no per-probe division, stores to nbr[k][base + j] coalesce across the lanes,
-    //     and per-tap pair counts come from one ballot per (warp, tap) instead of one atomic per pair.
-    const int warp = tid >> 5, lane = tid & 31;
-    const bool unit_stride = g.s[0] == 1 && g.s[1] == 1 && g.s[2] == 1;
-    for (int j0 = 0; j0 < cnt; j0 += 32) {
-        const int j = j0 + lane;
-        const bool has = j < cnt;
-        const int n = has ? s_vox[j] : 0;
-        // forward: S * c - pad (then + tap);  transposed: c + pad (then - tap, then / S)
-        int c[3] = {origin[0] + (n >> 6), origin[1] + ((n >> 3) & 7), origin[2] + (n & 7)};
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-            c[d] = transposed ? c[d] + g.pad[d] : g.s[d] * c[d] - g.pad[d];
-        for (int k = warp; k < k3; k += KM_THREADS / 32) {
-            int t[3];
-            if (small_taps) {
-                const uint32_t packed = s_tap[k];
-                t[0] = int(packed >> 20), t[1] = int((packed >> 10) & 1023), t[2] = int(packed & 1023);
-            } else {
-                t[0] = k / k12, t[1] = (k / g.k[2]) % g.k[1], t[2] = k % g.k[2];
-            }
-            int p[3];
-            bool ok = has;
-            if (!transposed) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                    p[d] = c[d] + t[d]; // fineFromCoarse
-            } else if (unit_stride) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                    p[d] = c[d] - t[d];
-            } else {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) { // coarseFromFine with the divisibility test
-                    const int numer = c[d] - t[d];
-                    ok = ok && floor_mod(numer, g.s[d]) == 0;
-                    p[d] = floor_div(numer, g.s[d]);
-                }
-            }
-            int val = -1;
-            if (ok) {
-                if (cached) {
-                    const int li = (((p[0] >> 3) - box.lmin[0]) * box.n[1] + ((p[1] >> 3) - box.lmin[1])) * box.n[2] +
-                                   ((p[2] >> 3) - box.lmin[2]);
-                    if (s_leaf[li] >= 0) {
-                        const int w = p[0] & 7;
-                        val = leaf_value(s_mask[li][w], s_prefix[li][w], s_base[li], p[1], p[2]);
-                    }
-                } else {
-                    val = lookup_row(feat, b, p[0], p[1], p[2]);
-                }
-            }
-            if (has)
-                nbr[int64_t(k) * pitch + base + j] = val;
-            const unsigned hits = __ballot_sync(0xffffffffu, val >= 0);
-            if (lane == 0 && hits) {
-                if (small_taps)
-                    s_cnt[k] += __popc(hits); // tap k belongs to this warp alone
+    const int leaf_id = blockIdx.x * KM_WARPS + warp;
+    if (leaf_id < out.num_leaves) {
+        const FvcLeaf *L = out.leaves + leaf_id;
+        const int b = __ldg(&L->batch);
+        const int origin[3] = {__ldg(&L->origin[0]), __ldg(&L->origin[1]), __ldg(&L->origin[2])};
+        const int base = __ldg(&L->base);
+        const int cnt = __ldg(&L->count);
+        const LeafBox box = probe_box(g, origin, transposed);
+        const bool cached = box.total <= KM_MAX_NB;
+
+        // (1) lanes walk the tree in parallel, one source leaf each
+        for (int t = lane; cached && t < box.total; t += 32) {
+            const int c = t % box.n[2], bb = (t / box.n[2]) % box.n[1], a = t / (box.n[2] * box.n[1]);
+            const int leaf = find_leaf(feat, b, (box.lmin[0] + a) << 3, (box.lmin[1] + bb) << 3, (box.lmin[2] + c) << 3);
+            s_leaf[warp][t] = leaf;
+            s_base[warp][t] = leaf >= 0 ? __ldg(&feat.leaves[leaf].base) : 0;
+        }
+        // (2) compact the output leaf's active voxels: rank inside the leaf == row - base.  Lane l scans 16 bits.
+        {
+            const int w = lane >> 2, shift = (lane & 3) * 16;
+            const uint64_t m = __ldg(L->mask + w);
+            const int before = int(__ldg(L->prefix + w)) + __popcll(m & ((1ull << shift) - 1ull));
+            uint32_t bits = uint32_t(m >> shift) & 0xFFFFu;
+            for (int r = before; bits; bits &= bits - 1u, ++r)
+                s_vox[warp][r] = uint16_t((w << 6) + shift + __ffs(bits) - 1);
+        }
+        __syncwarp();
+        // (3) stage mask (4 x 16 B) + prefix (1 x 16 B) of every source leaf
+        if (cached) {
+            for (int e = lane; e < box.total * 5; e += 32) {
+                const int li = e / 5, part = e % 5, leaf = s_leaf[warp][li];
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (leaf >= 0)
+                    v = __ldg(reinterpret_cast<const uint4 *>(feat.leaves + leaf) + part);
+                if (part < 4)
+                    reinterpret_cast<uint4 *>(&s_mask[warp][li][0])[part] = v;
                 else
-                    atomicAdd(tap_counts + k, (unsigned long long)__popc(hits));
+                    *reinterpret_cast<uint4 *>(&s_prefix[warp][li][0]) = v;
+            }
+        }
+        __syncwarp();
+
+        // (4) probes: a lane keeps one voxel's coordinates in registers and walks all taps; stores to nbr[k][base + j]
+        //     coalesce across the lanes; per-tap pair counts come from one ballot per tap.
+        const bool unit_stride = g.s[0] == 1 && g.s[1] == 1 && g.s[2] == 1;
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int j = j0 + lane;
+            const bool has = j < cnt;
+            const int n = has ? s_vox[warp][j] : 0;
+            // forward: S * c - pad (then + tap);  transposed: c + pad (then - tap, then / S)
+            int c[3] = {origin[0] + (n >> 6), origin[1] + ((n >> 3) & 7), origin[2] + (n & 7)};
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                c[d] = transposed ? c[d] + g.pad[d] : g.s[d] * c[d] - g.pad[d];
+            for (int k = 0; k < k3; ++k) {
+                int t[3];
+                if (small_taps) {
+                    const uint32_t packed = s_tap[k];
+                    t[0] = int(packed >> 20), t[1] = int((packed >> 10) & 1023), t[2] = int(packed & 1023);
+                } else {
+                    t[0] = k / k12, t[1] = (k / g.k[2]) % g.k[1], t[2] = k % g.k[2];
+                }
+                int p[3];
+                bool ok = has;
+                if (!transposed) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        p[d] = c[d] + t[d]; // fineFromCoarse
+                } else if (unit_stride) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        p[d] = c[d] - t[d];
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { // coarseFromFine with the divisibility test
+                        const int numer = c[d] - t[d];
+                        ok = ok && floor_mod(numer, g.s[d]) == 0;
+                        p[d] = floor_div(numer, g.s[d]);
+                    }
+                }
+                int val = -1;
+                if (ok) {
+                    if (cached) {
+                        const int li = (((p[0] >> 3) - box.lmin[0]) * box.n[1] + ((p[1] >> 3) - box.lmin[1])) * box.n[2] +
+                                       ((p[2] >> 3) - box.lmin[2]);
+                        if (s_leaf[warp][li] >= 0) {
+                            const int w = p[0] & 7;
+                            val = leaf_value(s_mask[warp][li][w], s_prefix[warp][li][w], s_base[warp][li], p[1], p[2]);
+                        }
+                    } else {
+                        val = lookup_row(feat, b, p[0], p[1], p[2]);
+                    }
+                }
+                if (has)
+                    nbr[int64_t(k) * pitch + base + j] = val;
+                const unsigned hits = __ballot_sync(0xffffffffu, val >= 0);
+                if (lane == 0 && hits) {
+                    if (small_taps)
+                        atomicAdd(&s_cnt[k], uint32_t(__popc(hits)));
+                    else
+                        atomicAdd(tap_counts + k, (unsigned long long)__popc(hits));
+                }
             }
         }
     }
@@ -421,7 +428,7 @@ int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_
     FVC_CUDA(cudaMemsetAsync(tap_counts, 0, size_t(g.volume) * 8, stream));
     if (output_grid->num_leaves == 0)
         return FVC_OK;
-    kmap_build_kernel<<<output_grid->num_leaves, KM_THREADS, 0, stream>>>(
+    kmap_build_kernel<<<unsigned(ceil_div(output_grid->num_leaves, KM_WARPS)), KM_THREADS, 0, stream>>>(
         *feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, reinterpret_cast<unsigned long long *>(tap_counts));
     FVC_LAUNCH_CHECK();
     return FVC_OK;
