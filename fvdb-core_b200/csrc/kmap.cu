@@ -14,8 +14,8 @@ namespace fvc {
 
 constexpr int KM_WARPS = 4;       // output leaves per CTA: one warp owns one leaf
 constexpr int KM_THREADS = KM_WARPS * 32;
-constexpr int KM_MAX_NB = 64;     // cached source leaves per output leaf (3x3x3 = 27 covers every K <= 9 stride-1 kernel)
-constexpr int KM_MAX_TAPS = 1024; // taps with shared-memory tap table / counters
+constexpr int KM_MAX_NB = 32;     // cached source leaves per output leaf (3x3x3 = 27 covers every K <= 9 stride-1 kernel)
+constexpr int KM_MAX_TAPS = 512;  // taps with shared-memory tap table / counters
 
 struct LeafBox {
     int lmin[3];
