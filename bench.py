@@ -297,16 +297,42 @@ def run_ours(args, cfg):
     gx_host = torch.empty((n, cin), dtype=dtype).pin_memory()
     gw_host = torch.empty(tuple(w.shape), dtype=dtype).pin_memory()
 
+    # three streams: host->device copies, kernels, device->host copies (PCIe is full duplex, so the read-back of
+    # y overlaps the upload of grad_out, and kernels overlap both)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
     def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)
-        dyd = dy_host.to(dev, non_blocking=True)
+        main = torch.cuda.current_stream(dev)
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            xd = x_host.to(dev, non_blocking=True)
+            x_ready = torch.cuda.Event()
+            x_ready.record(s_in)
+            dyd = dy_host.to(dev, non_blocking=True)
+            dy_ready = torch.cuda.Event()
+            dy_ready.record(s_in)
+        main.wait_event(x_ready)
         y = cpp.gs_conv(xd, w, topo)
+        y_done = torch.cuda.Event()
+        y_done.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(y_done)
+            y_host.copy_(y, non_blocking=True)
+        main.wait_event(dy_ready)
         gx, gw = cpp.gs_conv_backward(dyd, xd, w, topo)
         if world > 1:
             dist.all_reduce(gw)
-        y_host.copy_(y, non_blocking=True)
-        gx_host.copy_(gx, non_blocking=True)
-        gw_host.copy_(gw, non_blocking=True)
+        g_done = torch.cuda.Event()
+        g_done.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(g_done)
+            gx_host.copy_(gx, non_blocking=True)
+            gw_host.copy_(gw, non_blocking=True)
+        main.wait_stream(s_out)  # the step ends when its results are in host memory
+        for t in (xd, dyd):
+            t.record_stream(main)  # allocated on the copy-in stream, consumed by kernels on the main stream
+        for t in (y, gx, gw):
+            t.record_stream(s_out)  # allocated on the main stream, read by the copy-out stream
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
