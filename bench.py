@@ -68,6 +68,8 @@ def make_coords(cfg: dict, rank: int, device) -> list[torch.Tensor]:
         seed = rank * 1000 + g
         if cfg["gen"] == "random_occupancy":
             out.append(gen(seed=42 + seed, device=device))
+        elif cfg["gen"] == "lidar_sweep":  # ray casting vectorised on the device (scene parameters from a CPU generator)
+            out.append(gen(target=cfg["voxels"], seed=seed, device=device))
         else:
             out.append(gen(target=cfg["voxels"], seed=seed, device="cpu").to(device))
     return out
@@ -339,7 +341,7 @@ def run_ours(args, cfg):
             t.record_stream(s_out)  # allocated on the main stream, read by the copy-out stream
 
     e2e_mode = "3-stream overlap, whole batch"
-    if cpp.lib.fvc_conv_scratch_bytes(n, cin, cout, k3, code) > 0 and has_fixed_topology(plan):  # tensor-core path available
+    if cpp.lib.fvc_conv_scratch_bytes(n, n, cin, cout, k3, code) > 0 and dtype != torch.float32 and has_fixed_topology(plan):  # tensor-core path available
         from fvdb.streaming import HostPipelinedConv
 
         pipe = HostPipelinedConv(plan, num_chunks=8)

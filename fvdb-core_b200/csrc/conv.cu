@@ -18,8 +18,8 @@ static int check_common(const void *x, const void *w, int64_t n_in, int64_t n_ou
 
 extern "C" {
 
-size_t fvc_conv_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype) {
-    return tc_forward_supported(cin, cout, kernel_volume, dtype) ? tc_forward_scratch_bytes(n_out, cin, cout, kernel_volume, dtype) : 0;
+size_t fvc_conv_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype) {
+    return tc_forward_supported(cin, cout, kernel_volume, dtype) ? tc_forward_scratch_bytes(n_in, n_out, cin, cout, kernel_volume, dtype) : 0;
 }
 
 int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,

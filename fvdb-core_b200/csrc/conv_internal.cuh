@@ -47,9 +47,9 @@ int simt_wgrad(const WgradArgs &a);
 int wgrad_reduce_partials(const void *partial, int nchunks, int32_t cin, int32_t cout, int32_t k3, int32_t dtype, void *grad_w,
                           cudaStream_t stream);
 
-// tcgen05 path: f16/bf16, channel counts the UMMA tile shapes admit
+// tcgen05 path: f16/bf16 (and fp32 as a three-way bf16 split, forward/dgrad), channel counts the UMMA tile shapes admit
 bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
-size_t tc_forward_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
+size_t tc_forward_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
 int tc_forward(const ConvArgs &a);
 bool tc_wgrad_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
 size_t tc_wgrad_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);

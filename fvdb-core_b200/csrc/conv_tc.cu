@@ -1,4 +1,5 @@
-// conv_tc.cu -- tcgen05 / TMEM implicit-GEMM sparse convolution for f16 / bf16 (fp32 accumulate).
+// conv_tc.cu -- tcgen05 / TMEM implicit-GEMM sparse convolution for f16 / bf16 (fp32 accumulate) and for fp32
+// (three-way bf16 split, see "fp32 on the tensor pipe" below).
 //
 // Replaces PredGatherIGemm.cu (SM80 mma.sync TF32, forward only, one CTA per leaf) and the cuBLAS
 // gather -> mm -> atomic-scatter pipeline of GatherScatterDefault.cu:706-721,786-808 for the half types.
@@ -19,6 +20,14 @@
 // load.  The list of live (tap, channel block, tile) units is built once per CTA in shared memory; every role
 // walks that list, so the per-unit instruction stream stays short (clock64 instrumentation of the previous
 // version showed the role loops themselves -- not memory or the tensor pipe -- costing ~600 cycles per unit).
+//
+// fp32 on the tensor pipe (SPLIT = true).  An fp32 value is the exact sum of three bf16 values x = x0 + x1 + x2
+// (8 + 8 + 8 mantissa bits).  A pre-pass writes the split features [N][3][Cin] and the split weight image once per
+// call (N*Cin elements, not P*Cin); the executor gathers the three split rows like three channel blocks and issues
+//   x0.(w0 + w1 + w2)  +  x1.(w0 + w1)  +  x2.w0          (six bf16 products, exact in fp32; dropped terms <= 2^-24)
+// The x0.w0 term accumulates in its own TMEM columns and the five small terms (<= 2^-8 of it) in a second set, added
+// once in the epilogue: tcgen05 truncates on every accumulate (measured: -0.5 ulp per MMA on same-sign data,
+// scripts/exp_accum_precision.py), so the full-magnitude chain must stay as short as the bf16 one.
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
 
@@ -33,28 +42,37 @@ constexpr int TC_TILE_M = 128;
 constexpr int TC_A_BYTES = TC_TILE_M * 128; // one stage: 128 rows x 64 channels x 2 B
 constexpr int TC_MASK_WORDS = 8;            // tile tap-mask words (K^3 <= 512)
 constexpr int TC_MAX_UNITS = 4096;          // capacity of the per-CTA unit list (uint16 entries)
+constexpr int TC_MAX_UNITS_SPLIT = 2048;    // ... of the fp32 kernel (more shared memory goes to weight chunks)
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // Small channel counts are packed: a 64-wide reduction block holds G = 64 / CIN consecutive taps x CIN channels
 // ("tap group"), so Cin = 16 / 32 feed the same K = 64 pipeline (the bandwidth-bound small-channel path).
-template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW> struct TcFwdCfg {
+template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT = false> struct TcFwdCfg {
     static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per reduction block
     static constexpr int KB = CIN >= 64 ? CIN / 64 : 1;     // 64-wide reduction blocks per tap group
     static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a 128-byte row
-    static constexpr int B_BYTES = COUT * 128;               // one weight chunk: COUT rows x 64 channels x 2 B
-    static constexpr int TMEM_COLS = tmem_cols_for(TILES * COUT);
+    static constexpr int NS = SPLIT ? 3 : 1;                 // bf16 splits of an fp32 operand (A blocks and B chunks per (group, block))
+    static constexpr int XS = NS * CIN;                      // feature row stride in elements
+    static constexpr int CHUNK_BYTES = COUT * 128;           // one weight chunk: COUT rows x 64 channels x 2 B
+    static constexpr int B_BYTES = NS * CHUNK_BYTES;         // one weight stage: the chunk(s) of one (tap group, channel block)
+    static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * COUT;  // TMEM columns per tile (SPLIT: main | small-term accumulator)
+    static constexpr int TMEM_COLS = tmem_cols_for(TILES * ACC_COLS);
+    static constexpr int MAX_UNITS = SPLIT ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS;
     static constexpr int THREADS = (PW + 3) * 32;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * BST + 1 + 2 * TC_IDX_RING;
-    static constexpr int RING_BYTES = G * 512;               // one ring entry: 128 map entries per tap of the group
+    // one ring entry: 128 map entries per tap of the group; with several taps per entry each tap's 512 bytes are followed
+    // by a 16-byte pad, so the four taps a quarter-warp reads together sit on different banks
+    static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;
+    static constexpr int RING_BYTES = G * SUB_STRIDE;
     static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TC_IDX_RING) * RING_BYTES +
-                                   size_t(TC_MAX_UNITS) * 2 + 8 * NUM_BARS + 16;
+                                   size_t(MAX_UNITS) * 2 + 8 * NUM_BARS + 16;
     // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (228 KB per SM, 1 KB reserved per CTA)
     static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = int(233472 / (SMEM + 1024 + 768));
     static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > 2 ? 2 : BY_TMEM) : (BY_SMEM > 2 ? 2 : BY_SMEM);
     static_assert(CTAS_PER_SM >= 1, "configuration does not fit one SM");
     static_assert((CIN % 64 == 0 || CIN == 32 || CIN == 16) && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
-    static_assert(TILES * COUT <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
+    static_assert(TILES * ACC_COLS <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
     static_assert(PW == 4 || PW == 8, "producer warps");
 };
 
@@ -86,6 +104,73 @@ __global__ void tc_pack_b_kernel(const uint16_t *__restrict__ w /*[k3][cin][cout
     }
 }
 
+// x = s0 + s1 + s2 with every s_i a bf16 (round-to-nearest each time; the remainders are exact in fp32)
+__device__ __forceinline__ void split3(float v, uint16_t (&out)[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[i] = *reinterpret_cast<const uint16_t *>(&h);
+        v -= __bfloat162float(h);
+    }
+}
+
+// fp32 rows [n][c] -> bf16 split rows [n][3][c]; one thread per 8 consecutive channels (32 B in, 3 x 16 B out)
+__global__ void tc_split_rows_kernel(const float *__restrict__ x, int64_t n, int c, uint16_t *__restrict__ xs) {
+    const int c8 = c >> 3;
+    const int64_t total = n * c8;
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t row = e / c8;
+        const int ch = int(e - row * c8) * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(x + row * c + ch)), b = __ldg(reinterpret_cast<const float4 *>(x + row * c + ch) + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t packed[3][4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint16_t lo[3], hi[3];
+            split3(v[2 * h], lo);
+            split3(v[2 * h + 1], hi);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                packed[i][h] = uint32_t(lo[i]) | (uint32_t(hi[i]) << 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            *reinterpret_cast<uint4 *>(xs + (row * 3 + i) * c + ch) = make_uint4(packed[i][0], packed[i][1], packed[i][2], packed[i][3]);
+    }
+}
+
+// Split weight image: like tc_pack_b_kernel, but chunk c = (group * KB + j) * 3 + i holds split i of the fp32 weights.
+__global__ void tc_pack_b_split_kernel(const float *__restrict__ w /*[k3][cin][cout]*/, int k3, int cin, int cout,
+                                       uint4 *__restrict__ img) {
+    const int g = cin >= 64 ? 1 : 64 / cin, kb = cin >= 64 ? cin / 64 : 1;
+    const int groups = (k3 + g - 1) / g;
+    const int64_t total = int64_t(groups) * kb * 3 * cout * 8; // 16-byte chunks
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+        const int pos = int(e & 7);
+        const int n = int((e >> 3) % cout);
+        const int64_t chunk3 = (e >> 3) / cout;
+        const int i = int(chunk3 % 3);
+        const int64_t chunk = chunk3 / 3;
+        const int j = int(chunk % kb), group = int(chunk / kb);
+        const int q = pos ^ (n & 7);
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        const int kk0 = q * 8;
+        const int tap = cin >= 64 ? group : group * g + kk0 / cin;
+        const int ci0 = cin >= 64 ? j * 64 + kk0 : kk0 % cin;
+        if (tap < k3) {
+            const float *src = w + (int64_t(tap) * cin + ci0) * cout + n;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                uint16_t lo[3], hi[3];
+                split3(src[int64_t(2 * h) * cout], lo);
+                split3(src[int64_t(2 * h + 1) * cout], hi);
+                v[h] = uint32_t(lo[i]) | (uint32_t(hi[i]) << 16);
+            }
+        }
+        img[e] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b, bool bf16) {
     if (bf16) {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -98,13 +183,14 @@ __device__ __forceinline__ float half_to_float(uint16_t v, bool bf16) {
     return bf16 ? __bfloat162float(*reinterpret_cast<__nv_bfloat16 *>(&v)) : __half2float(*reinterpret_cast<__half *>(&v));
 }
 
-template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW>
-__global__ void __launch_bounds__((PW + 3) * 32, (TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW>::CTAS_PER_SM))
-conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_img, const uint16_t *__restrict__ bias,
-                   uint16_t *__restrict__ y, const int32_t *__restrict__ nbr, int64_t pitch,
+// x: feature rows (SPLIT: the bf16 split rows [N][3][CIN]); bias / y: in the output dtype (SPLIT: fp32)
+template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT>
+__global__ void __launch_bounds__((PW + 3) * 32, (TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>::CTAS_PER_SM))
+conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_img, const void *__restrict__ bias_,
+                   void *__restrict__ y_, const int32_t *__restrict__ nbr, int64_t pitch,
                    const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, uint32_t idesc, int is_bf16) {
-    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW>;
-    constexpr int KB = Cfg::KB, G = Cfg::G, CPT = Cfg::CPT, THREADS = Cfg::THREADS;
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>;
+    constexpr int KB = Cfg::KB, G = Cfg::G, CPT = Cfg::CPT, THREADS = Cfg::THREADS, NS = Cfg::NS, XS = Cfg::XS, ACC = Cfg::ACC_COLS;
     constexpr int WARP_MMA = PW, WARP_B = PW + 1;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
@@ -112,7 +198,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
     const uint32_t smem_idx = smem_b + BST * Cfg::B_BYTES;
     const uint32_t smem_units = smem_idx + TC_IDX_RING * Cfg::RING_BYTES;
-    const uint32_t bars = smem_units + TC_MAX_UNITS * 2;
+    const uint32_t bars = smem_units + Cfg::MAX_UNITS * 2;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 8 * BST;
     const uint32_t bar_accum = bar_bempty + 8 * BST;
@@ -166,13 +252,13 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     if (warp == WARP_MMA)
         tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     __syncthreads();
-    if (warp == 0) { // unit list in [tap group][channel block][tile] order: entry = group << 5 | block << 3 | tile
+    if (warp == 0) { // unit list in [tap group][channel block][split][tile] order: entry = group << 7 | block << 5 | split << 3 | tile
         int base = 0;
         uint32_t live = 0;
         for (int k0 = 0; k0 < ngroups; k0 += 32) {
             const int k = k0 + lane;
             const uint32_t bits = k < ngroups ? s_tiles[k] : 0u;
-            const int cnt = KB * __popc(bits);
+            const int cnt = KB * NS * __popc(bits);
             int incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -182,8 +268,9 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             }
             int off = base + incl - cnt;
             for (int j = 0; j < KB; ++j)
-                for (uint32_t rest = bits; rest; rest &= rest - 1u)
-                    units[off++] = uint16_t((k << 5) | (j << 3) | (__ffs(rest) - 1));
+                for (int i = 0; i < NS; ++i)
+                    for (uint32_t rest = bits; rest; rest &= rest - 1u)
+                        units[off++] = uint16_t((k << 7) | (j << 5) | (i << 3) | (__ffs(rest) - 1));
             base += __shfl_sync(0xffffffffu, incl, 31);
             live |= bits;
         }
@@ -202,36 +289,45 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const int nunits = s_nunits;
 
     if (warp < PW) {
-        // ================= gather producers: warp w copies rows [RPW*w, RPW*(w+1)), 4 rows per instruction =================
+        // ================= gather producers: warp w copies rows [RPW*w, RPW*(w+1)) =================
+        // lane = (g, q): 8 lanes q cover one 128-byte row (one full line); lane group g owns the NI CONSECUTIVE rows
+        // row0 .. row0 + NI - 1, so its map entries are NI contiguous int32 (128-bit shared loads) and instruction i
+        // of the warp copies rows {row0(g) + i}.
         constexpr int RPW = TC_TILE_M / PW, NI = RPW / 4;
         const int q = lane & 7;
-        const int my_row = warp * RPW + (lane >> 3);          // rows my_row + 4i, i < NI
-        const uint32_t dst0 = uint32_t(my_row) * 128u;
-        const uint32_t swz0 = uint32_t(q ^ (my_row & 7)) << 4, swz1 = uint32_t(q ^ ((my_row & 7) ^ 4)) << 4;
+        const int row0 = warp * RPW + (lane >> 3) * NI;
         // lane q copies 16-byte chunk q of each of its rows; with packed taps (Cin < 64) that chunk belongs to tap
         // `sub` of the group and to channel chunk q % CPT of that tap's feature row
         const int sub = q / CPT;
         const uint16_t *xq = x + (CIN >= 64 ? q * 8 : (q % CPT) * 8);
+        uint32_t dst_off[NI]; // row offset + swizzled chunk position inside a stage
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+            dst_off[i] = uint32_t(row0 + i) * 128u + (uint32_t(q ^ ((row0 + i) & 7)) << 4);
+        const uint32_t idx_src = smem_idx + sub * Cfg::SUB_STRIDE + row0 * 4;
         int s = 0;
         uint32_t ph = 0;
         for (int u = 0; u < nunits; ++u) {
             const uint32_t unit = units[u];
-            const int g = int(unit >> 5), j = (unit >> 3) & 3, t = unit & 7;
+            const int g = int(unit >> 7), j = (unit >> 5) & 3, t = unit & 7;
             const int e = u & (TC_IDX_RING - 1);
             mbar_wait(bar_ifull + 8 * e, (u / TC_IDX_RING) & 1);
             int idx[NI];
 #pragma unroll
-            for (int i = 0; i < NI; ++i)
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx[i]) : "r"(smem_idx + e * Cfg::RING_BYTES + sub * 512 + (my_row + 4 * i) * 4) : "memory");
-            // row my_row + 4i exists iff 4i < rows_left; a tap beyond the kernel volume (last, partial group) is empty
-            const int64_t rows_left = (G == 1 || g * G + sub < k3) ? n_out - (tile0 + t) * TC_TILE_M - my_row : 0;
+            for (int i = 0; i < NI; i += 4)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(idx[i]), "=r"(idx[i + 1]), "=r"(idx[i + 2]), "=r"(idx[i + 3])
+                             : "r"(idx_src + e * Cfg::RING_BYTES + i * 4)
+                             : "memory");
+            // row row0 + i exists iff i < rows_left; a tap beyond the kernel volume (last, partial group) is empty
+            const int64_t rows_left = (G == 1 || g * G + sub < k3) ? n_out - (tile0 + t) * TC_TILE_M - row0 : 0;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-            const uint32_t dst = smem_a + s * TC_A_BYTES + dst0;
-            const uint16_t *xj = xq + j * 64;
+            const uint32_t dst = smem_a + s * TC_A_BYTES;
+            const uint16_t *xj = xq + j * 64 + (SPLIT ? int((unit >> 3) & 3u) * CIN : 0);
 #pragma unroll
-            for (int i = 0; i < NI; ++i) { // 8 lanes cover one 128-byte row (one full line)
-                const bool ok = idx[i] >= 0 && 4 * i < rows_left;
-                cp_async16(dst + i * 512 + ((i & 1) ? swz1 : swz0), ok ? xj + int64_t(idx[i]) * CIN : x, ok ? 16u : 0u);
+            for (int i = 0; i < NI; ++i) {
+                const bool ok = idx[i] >= 0 && i < rows_left;
+                cp_async16(dst + dst_off[i], ok ? xj + int64_t(idx[i]) * XS : x, ok ? 16u : 0u);
             }
             __syncwarp();
             if (lane == 0)
@@ -259,32 +355,58 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             for (int c0 = 0; c0 < COUT; c0 += EC) {
                 uint32_t acc[32];
                 if ((live >> tt) & 1u) {
-                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(tt * COUT + c0);
+                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(tt * ACC + c0);
                     if (EC == 32)
                         tmem_ld_32x32b_x32(taddr, acc);
                     else
                         tmem_ld_32x32b_x16(taddr, acc);
-                    tmem_ld_wait();
+                    if (SPLIT) { // + the small-term accumulator (one rounded fp32 add per output)
+                        uint32_t small[32];
+                        if (EC == 32)
+                            tmem_ld_32x32b_x32(taddr + COUT, small);
+                        else
+                            tmem_ld_32x32b_x16(taddr + COUT, small);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int z = 0; z < EC; ++z)
+                            acc[z] = __float_as_uint(__uint_as_float(acc[z]) + __uint_as_float(small[z]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                 } else { // a tile no tap reaches was never accumulated: its rows are zero (+ bias)
 #pragma unroll
                     for (int z = 0; z < 32; ++z)
                         acc[z] = 0u;
                 }
                 if (row < n_out) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(y + row * COUT + c0);
+                    if (SPLIT) {
+                        const float *bias = reinterpret_cast<const float *>(bias_);
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<float *>(y_) + row * COUT + c0);
 #pragma unroll
-                    for (int v4 = 0; v4 < EC / 8; ++v4) {
-                        uint32_t p[4];
+                        for (int v4 = 0; v4 < EC / 4; ++v4) {
+                            uint32_t p[4];
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            float a = __uint_as_float(acc[v4 * 8 + 2 * h]), b = __uint_as_float(acc[v4 * 8 + 2 * h + 1]);
-                            if (bias) {
-                                a += half_to_float(bias[c0 + v4 * 8 + 2 * h], bf16);
-                                b += half_to_float(bias[c0 + v4 * 8 + 2 * h + 1], bf16);
-                            }
-                            p[h] = pack_half2(a, b, bf16);
+                            for (int h = 0; h < 4; ++h)
+                                p[h] = bias ? __float_as_uint(__uint_as_float(acc[v4 * 4 + h]) + __ldg(bias + c0 + v4 * 4 + h)) : acc[v4 * 4 + h];
+                            dst[v4] = make_uint4(p[0], p[1], p[2], p[3]);
                         }
-                        dst[v4] = make_uint4(p[0], p[1], p[2], p[3]);
+                    } else {
+                        const uint16_t *bias = reinterpret_cast<const uint16_t *>(bias_);
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(y_) + row * COUT + c0);
+#pragma unroll
+                        for (int v4 = 0; v4 < EC / 8; ++v4) {
+                            uint32_t p[4];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                float a = __uint_as_float(acc[v4 * 8 + 2 * h]), b = __uint_as_float(acc[v4 * 8 + 2 * h + 1]);
+                                if (bias) {
+                                    a += half_to_float(bias[c0 + v4 * 8 + 2 * h], bf16);
+                                    b += half_to_float(bias[c0 + v4 * 8 + 2 * h + 1], bf16);
+                                }
+                                p[h] = pack_half2(a, b, bf16);
+                            }
+                            dst[v4] = make_uint4(p[0], p[1], p[2], p[3]);
+                        }
                     }
                 }
             }
@@ -296,11 +418,11 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             const uint64_t desc_hi = make_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | (1u << 16);
             int s = 0, c = -1, prev_kj = -1;
-            uint32_t ph = 0, started = 0, b_lo = 0;
+            uint32_t ph = 0, started = 0, started_small = 0, b_lo = 0;
             for (int u = 0; u < nunits; ++u) {
                 const uint32_t unit = units[u];
-                const int kj = int(unit >> 3), t = unit & 7;
-                if (kj != prev_kj) { // next weight chunk
+                const int kj = int(unit >> 5), t = unit & 7;
+                if (kj != prev_kj) { // next weight stage
                     if (c >= 0)
                         umma_commit(bar_bempty + 8 * (c % BST));
                     ++c;
@@ -311,11 +433,29 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + uint32_t(s) * (TC_A_BYTES >> 4);
-                const uint32_t acc0 = (started >> t) & 1u;
+                if (!SPLIT) {
+                    const uint32_t acc0 = (started >> t) & 1u;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) // 4 x K=16 inside the 128-byte swizzle span (+32 B = +2 descriptor units)
-                    umma_f16(tmem_base + uint32_t(t * COUT), desc_hi | (a_lo + 2 * kk), desc_hi | (b_lo + 2 * kk), idesc,
-                             acc0 | uint32_t(kk != 0));
+                    for (int kk = 0; kk < 4; ++kk) // 4 x K=16 inside the 128-byte swizzle span (+32 B = +2 descriptor units)
+                        umma_f16(tmem_base + uint32_t(t * ACC), desc_hi | (a_lo + 2 * kk), desc_hi | (b_lo + 2 * kk), idesc,
+                                 acc0 | uint32_t(kk != 0));
+                } else {
+                    // split i of the features meets weight splits 0 .. 2 - i; only x0.w0 goes to the main accumulator
+                    const int i = int((unit >> 3) & 3u);
+                    for (int jj = 0; jj + i <= 2; ++jj) {
+                        const bool main_term = (i | jj) == 0;
+                        const uint32_t acc0 = ((main_term ? started : started_small) >> t) & 1u;
+                        const uint32_t d = tmem_base + uint32_t(t * ACC + (main_term ? 0 : COUT));
+                        const uint32_t bj = b_lo + uint32_t(jj) * (Cfg::CHUNK_BYTES >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_f16(d, desc_hi | (a_lo + 2 * kk), desc_hi | (bj + 2 * kk), idesc, acc0 | uint32_t(kk != 0));
+                        if (main_term)
+                            started |= 1u << t;
+                        else
+                            started_small |= 1u << t;
+                    }
+                }
                 umma_commit(bar_empty + 8 * s); // stage reusable once these MMAs retire
                 started |= 1u << t;
                 if (++s == STAGES) {
@@ -332,7 +472,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             int c = 0, prev_kj = -1;
             for (int u = 0; u < nunits; ++u) {
                 const uint32_t unit = units[u];
-                const int kj = int(unit >> 3);
+                const int kj = int(unit >> 5);
                 if (kj == prev_kj)
                     continue;
                 prev_kj = kj;
@@ -350,13 +490,13 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         const int32_t *lane_nbr = nbr + tile0 * TC_TILE_M + lane * 4;
         for (int u = 0; u < nunits; ++u) {
             const uint32_t unit = units[u];
-            const int g = int(unit >> 5), t = unit & 7;
+            const int g = int(unit >> 7), t = unit & 7;
             const int e = u & (TC_IDX_RING - 1);
             mbar_wait(bar_iempty + 8 * e, ((u / TC_IDX_RING) & 1) ^ 1);
 #pragma unroll
             for (int sub = 0; sub < G; ++sub)
                 if (g * G + sub < k3)
-                    cp_async16(smem_idx + e * Cfg::RING_BYTES + sub * 512 + lane * 16, lane_nbr + int64_t(g * G + sub) * pitch + t * TC_TILE_M, 16u);
+                    cp_async16(smem_idx + e * Cfg::RING_BYTES + sub * Cfg::SUB_STRIDE + lane * 16, lane_nbr + int64_t(g * G + sub) * pitch + t * TC_TILE_M, 16u);
             cp_async_arrive_noinc(bar_ifull + 8 * e);
         }
         cp_async_wait_all();
@@ -368,83 +508,133 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW> static int launch_tc_fwd(const ConvArgs &a, const uint8_t *w_img) {
-    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW>;
-    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES, BST, PW>;
+static inline int tc_groups(int64_t k3, int32_t cin) { return cin >= 64 ? int(k3) : int(ceil_div(k3, 64 / cin)); }
+static inline size_t tc_image_bytes(int32_t cin, int32_t cout, int64_t k3, int splits) {
+    const int64_t kb = cin >= 64 ? cin / 64 : 1;
+    return align_up(size_t(tc_groups(k3, cin)) * size_t(kb) * size_t(splits) * size_t(cout) * 128, 256);
+}
+
+template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT = false>
+static int launch_tc_fwd(const ConvArgs &a, const void *x, const uint8_t *w_img) {
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>;
+    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>;
     static bool configured = false; // per instantiation
     if (!configured) {
         FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
         configured = true;
     }
-    FVC_REQUIRE(ceil_div(a.k3, Cfg::G) * Cfg::KB * TILES <= TC_MAX_UNITS, FVC_ERR_UNSUPPORTED, "kernel volume %d too large for the tensor-core unit list", a.k3);
+    FVC_REQUIRE(ceil_div(a.k3, Cfg::G) * Cfg::KB * Cfg::NS * TILES <= Cfg::MAX_UNITS, FVC_ERR_UNSUPPORTED,
+                "kernel volume %d too large for the tensor-core unit list", a.k3);
     const int64_t tiles = ceil_div(a.n_out, TC_TILE_M);
     const unsigned grid = unsigned(ceil_div(tiles, TILES));
-    const bool bf16 = a.dtype == FVC_BF16;
+    const bool bf16 = SPLIT || a.dtype == FVC_BF16;
     const uint32_t idesc = make_idesc_f16(TC_TILE_M, COUT, bf16, false, false);
-    kernel<<<grid, Cfg::THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), w_img,
-                                                        reinterpret_cast<const uint16_t *>(a.bias), reinterpret_cast<uint16_t *>(a.y),
-                                                        a.nbr, a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out,
-                                                        a.k3, idesc, bf16 ? 1 : 0);
+    kernel<<<grid, Cfg::THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(x), w_img, a.bias, a.y, a.nbr, a.pitch,
+                                                        reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out, a.k3, idesc,
+                                                        bf16 ? 1 : 0);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }
 
-static inline int tc_groups(int64_t k3, int32_t cin) { return cin >= 64 ? int(k3) : int(ceil_div(k3, 64 / cin)); }
+static inline bool tc_channels_ok(int32_t c, int32_t max_c) { return (c == 16 || c == 32 || c == 64 || c == 128 || c == 256) && c <= max_c; }
 
 bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
-    if (dtype != FVC_F16 && dtype != FVC_BF16)
+    const bool split = dtype == FVC_F32;
+    if (dtype != FVC_F16 && dtype != FVC_BF16 && !split)
         return false;
-    const bool cin_ok = cin == 16 || cin == 32 || cin == 64 || cin == 128 || cin == 256;
-    const bool cout_ok = cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256;
-    if (!cin_ok || !cout_ok)
+    if (!tc_channels_ok(cin, 256) || !tc_channels_ok(cout, split ? 128 : 256))
         return false;
     const int64_t kb = cin >= 64 ? cin / 64 : 1;
-    return k3 >= 1 && k3 <= 64 * TC_MASK_WORDS && tc_groups(k3, cin) * kb * 8 <= TC_MAX_UNITS;
+    const int64_t units = tc_groups(k3, cin) * kb * (split ? 3 : 1) * 8;
+    return k3 >= 1 && k3 <= 64 * TC_MASK_WORDS && units <= (split ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS);
 }
 
-size_t tc_forward_scratch_bytes(int64_t, int32_t cin, int32_t cout, int64_t k3, int32_t) {
-    const int64_t kb = cin >= 64 ? cin / 64 : 1;
-    return size_t(tc_groups(k3, cin)) * size_t(kb) * size_t(cout) * 128 + 256;
+// scratch = [weight image | split feature rows (fp32 only)]
+size_t tc_forward_scratch_bytes(int64_t n_in, int64_t, int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
+    if (dtype == FVC_F32)
+        return tc_image_bytes(cin, cout, k3, 3) + align_up(size_t(n_in > 0 ? n_in : 0) * 3 * size_t(cin) * 2, 256) + 256;
+    return tc_image_bytes(cin, cout, k3, 1) + 256;
+}
+
+static int tc_forward_split(const ConvArgs &a) {
+    uint8_t *img = reinterpret_cast<uint8_t *>(a.scratch);
+    uint16_t *xs = reinterpret_cast<uint16_t *>(img + tc_image_bytes(a.cin, a.cout, a.k3, 3));
+    const int64_t chunks16 = int64_t(tc_groups(a.k3, a.cin)) * (a.cin >= 64 ? a.cin / 64 : 1) * 3 * a.cout * 8;
+    tc_pack_b_split_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
+        reinterpret_cast<const float *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
+    FVC_LAUNCH_CHECK();
+    const int64_t work = a.n_in * (a.cin / 8);
+    if (work > 0) {
+        tc_split_rows_kernel<<<int(ceil_div(work, 256) > 148 * 16 ? 148 * 16 : ceil_div(work, 256)), 256, 0, a.stream>>>(
+            reinterpret_cast<const float *>(a.x), a.n_in, a.cin, xs);
+        FVC_LAUNCH_CHECK();
+    }
+#define FVC_TCS_CASE(CI, CO, T, S, B) \
+    if (a.cin == CI && a.cout == CO)  \
+        return launch_tc_fwd<CI, CO, T, S, B, 4, true>(a, xs, img);
+#define FVC_TCS_CIN(CI)           \
+    FVC_TCS_CASE(CI, 16, 8, 4, 3)  \
+    FVC_TCS_CASE(CI, 32, 4, 4, 3)  \
+    FVC_TCS_CASE(CI, 64, 2, 3, 2)  \
+    FVC_TCS_CASE(CI, 128, 1, 3, 2)
+    FVC_TCS_CIN(16)
+    FVC_TCS_CIN(32)
+    FVC_TCS_CIN(64)
+    FVC_TCS_CIN(128)
+    FVC_TCS_CIN(256)
+#undef FVC_TCS_CIN
+#undef FVC_TCS_CASE
+    return set_error(FVC_ERR_UNSUPPORTED, "no fp32 tensor-core kernel for channels %d -> %d", a.cin, a.cout);
 }
 
 int tc_forward(const ConvArgs &a) {
-    const size_t need = tc_forward_scratch_bytes(a.n_out, a.cin, a.cout, a.k3, a.dtype);
+    const size_t need = tc_forward_scratch_bytes(a.n_in, a.n_out, a.cin, a.cout, a.k3, a.dtype);
     FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core conv scratch too small: %zu < %zu",
                 a.scratch_bytes, need);
     FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.nbr) & 15) == 0,
-                FVC_ERR_RUNTIME, "tensor-core conv needs 16-byte aligned feature / output / scratch / map pointers");
+                    (reinterpret_cast<uintptr_t>(a.scratch) & 255) == 0 && (reinterpret_cast<uintptr_t>(a.nbr) & 15) == 0,
+                FVC_ERR_RUNTIME, "tensor-core conv needs 16-byte aligned feature / output / map pointers and 256-byte aligned scratch");
     FVC_REQUIRE(a.pitch % 4 == 0 && a.pitch >= ceil_div(a.n_out, TC_TILE_M) * TC_TILE_M, FVC_ERR_RUNTIME,
                 "tensor-core conv needs the map pitch (%lld) to be a multiple of 4 covering whole 128-row tiles", (long long)a.pitch);
+    if (a.dtype == FVC_F32)
+        return tc_forward_split(a);
     uint8_t *img = reinterpret_cast<uint8_t *>(a.scratch);
     const int64_t chunks16 = int64_t(tc_groups(a.k3, a.cin)) * (a.cin >= 64 ? a.cin / 64 : 1) * a.cout * 8;
     tc_pack_b_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
         reinterpret_cast<const uint16_t *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
     FVC_LAUNCH_CHECK();
-    // experiment knob (scripts/bench_variants.py): alternative pipeline shapes for the 64 -> 64 kernel
+    // experiment knob (scripts/bench_variants.py): alternative pipeline shapes
+    const char *variant_env = getenv("FVC_TC_VARIANT");
+    const int variant = variant_env ? atoi(variant_env) : 0;
     if (a.cin == 64 && a.cout == 64) {
-        const char *v = getenv("FVC_TC_VARIANT");
-        switch (v ? atoi(v) : 0) {
-        case 1: return launch_tc_fwd<64, 64, 4, 4, 3, 8>(a, img);
-        case 2: return launch_tc_fwd<64, 64, 8, 8, 4, 4>(a, img);
-        case 3: return launch_tc_fwd<64, 64, 4, 3, 3, 4>(a, img);
-        case 4: return launch_tc_fwd<64, 64, 2, 4, 3, 4>(a, img);
+        switch (variant) {
+        case 1: return launch_tc_fwd<64, 64, 4, 4, 3, 8>(a, a.x, img);
+        case 2: return launch_tc_fwd<64, 64, 8, 8, 4, 4>(a, a.x, img);
+        case 3: return launch_tc_fwd<64, 64, 4, 3, 3, 4>(a, a.x, img);
+        case 4: return launch_tc_fwd<64, 64, 2, 4, 3, 4>(a, a.x, img);
         default: break;
         }
     }
     if (a.cin == 128 && a.cout == 128) {
-        const char *v = getenv("FVC_TC_VARIANT");
-        switch (v ? atoi(v) : 0) {
-        case 1: return launch_tc_fwd<128, 128, 2, 3, 2, 4>(a, img);
-        case 2: return launch_tc_fwd<128, 128, 4, 6, 4, 4>(a, img);
-        case 3: return launch_tc_fwd<128, 128, 4, 8, 3, 8>(a, img);
-        case 4: return launch_tc_fwd<128, 128, 2, 4, 2, 4>(a, img);
+        switch (variant) {
+        case 1: return launch_tc_fwd<128, 128, 2, 3, 2, 4>(a, a.x, img);
+        case 2: return launch_tc_fwd<128, 128, 4, 6, 4, 4>(a, a.x, img);
+        case 3: return launch_tc_fwd<128, 128, 4, 8, 3, 8>(a, a.x, img);
+        case 4: return launch_tc_fwd<128, 128, 2, 4, 2, 4>(a, a.x, img);
+        default: break;
+        }
+    }
+    if (a.cin == 16 && a.cout == 16) {
+        switch (variant) {
+        case 1: return launch_tc_fwd<16, 16, 8, 5, 3, 4>(a, a.x, img);
+        case 2: return launch_tc_fwd<16, 16, 8, 4, 3, 8>(a, a.x, img);
+        case 3: return launch_tc_fwd<16, 16, 4, 5, 3, 4>(a, a.x, img);
         default: break;
         }
     }
 #define FVC_TC_CASE(CI, CO, T, S, B) \
     if (a.cin == CI && a.cout == CO) \
-        return launch_tc_fwd<CI, CO, T, S, B, 4>(a, img);
+        return launch_tc_fwd<CI, CO, T, S, B, 4>(a, a.x, img);
 #define FVC_TC_CIN(CI)           \
     FVC_TC_CASE(CI, 16, 8, 4, 3)  \
     FVC_TC_CASE(CI, 32, 8, 4, 3)  \

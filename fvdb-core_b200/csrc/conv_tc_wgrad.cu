@@ -36,7 +36,8 @@ template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
     static constexpr int BQ = COUT >= 64 ? 8 : COUT / 8;    // valid 16-byte chunks of a dY row per B block
     static constexpr int MAX_UNITS = 512 / NPAD;            // accumulators that fit TMEM
     static constexpr int RING = G == 4 ? 4 : 8;             // kernel-map ring depth
-    static constexpr int RING_BYTES = 2 * G * 512;          // two blocks x G taps x 128 int32
+    static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;    // 128 int32 per tap (+ a 16-byte pad so packed taps sit on different banks)
+    static constexpr int RING_BYTES = 2 * G * SUB_STRIDE;   // two blocks x G taps
     static constexpr int A_STAGE = 2 * WG_BLOCK_BYTES;
     static constexpr int B_STAGE = NB * WG_BLOCK_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * RING;
@@ -46,15 +47,20 @@ template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
-// One warp's share (rows [32w, 32w+32)) of a 128-row x 128-byte swizzled block: 8 lanes cover one row (one full
-// 128-byte line), 4 rows per instruction; idx[i] < 0 zero-fills row 32w + 4i + (lane >> 3).
-__device__ __forceinline__ void gather_rows(uint32_t dst /* block + my_row * 128 */, uint32_t swz0, uint32_t swz1,
+// One warp's share (rows [32w, 32w+32)) of a 128-row x 128-byte swizzled block: 8 lanes q cover one row (one full
+// 128-byte line); lane group g = lane >> 3 owns the 8 consecutive rows row0 = 32w + 8g .. row0 + 7 (row0 is a multiple
+// of 8, so row i's swizzle term is i); idx[i] < 0 zero-fills row row0 + i.
+__device__ __forceinline__ void gather_rows(uint32_t dst /* block + row0 * 128 */, int q,
                                             const uint16_t *__restrict__ base /* + column offset */, int64_t row_stride,
                                             const int (&idx)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        cp_async16(dst + i * 512 + ((i & 1) ? swz1 : swz0), idx[i] >= 0 ? base + int64_t(idx[i]) * row_stride : base,
+        cp_async16(dst + i * 128 + (uint32_t(q ^ i) << 4), idx[i] >= 0 ? base + int64_t(idx[i]) * row_stride : base,
                    idx[i] >= 0 ? 16u : 0u);
+}
+__device__ __forceinline__ void lds_v4x2(uint32_t addr, int (&v)[8]) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr + 16) : "memory");
 }
 
 template <int CIN, int COUT, int STAGES>
@@ -147,14 +153,13 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     if (warp < WG_PW) {
         // ================= producers: dY tile, then the gathered X blocks of every live unit =================
         const int q = lane & 7, sub = q / CPT;
-        const int my_row = warp * 32 + (lane >> 3); // rows my_row + 4i, i < 8
-        const uint32_t dst0 = uint32_t(my_row) * 128u;
-        const uint32_t swz0 = uint32_t(q ^ (my_row & 7)) << 4, swz1 = uint32_t(q ^ ((my_row & 7) ^ 4)) << 4;
+        const int row0 = warp * 32 + (lane >> 3) * 8; // rows row0 + i, i < 8
+        const uint32_t dst0 = uint32_t(row0) * 128u;
         const uint16_t *xq = x + (CIN >= 64 ? q * 8 : (q % CPT) * 8), *dyq = dy + q * 8;
         int s = 0, e = 0, tb = 0;
         uint32_t ph = 0, eph = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
-            const int64_t rows_left = n_out - tile * WG_TILE - my_row; // row my_row + 4i exists iff 4i < rows_left
+            const int64_t rows_left = n_out - tile * WG_TILE - row0; // row row0 + i exists iff i < rows_left
             const uint32_t live = live_units(tile);
             { // B: plain rows of dY (identity "map"); lanes beyond a narrow row's chunks zero-fill
                 const int bs = tb & 1;
@@ -162,10 +167,10 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 int self[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    self[i] = (4 * i < rows_left && q < Cfg::BQ) ? int(tile * WG_TILE + my_row + 4 * i) : -1;
+                    self[i] = (i < rows_left && q < Cfg::BQ) ? int(tile * WG_TILE + row0 + i) : -1;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb)
-                    gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES + dst0, swz0, swz1, dyq + nb * 64, COUT, self);
+                    gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES + dst0, q, dyq + nb * 64, COUT, self);
                 cp_async_arrive_noinc(bar_bfull + 8 * bs);
             }
             for (uint32_t rest = live; rest; rest &= rest - 1u) {
@@ -174,20 +179,20 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 int idx0[8], idx1[8];
                 const bool ok0 = first_tap(blk) + sub < k3;
                 const bool ok1 = blk + 1 < total_blocks && first_tap(blk + 1) + sub < k3; // odd block count: zero dummy
+                const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * Cfg::SUB_STRIDE + row0 * 4;
+                lds_v4x2(entry, idx0);
+                lds_v4x2(entry + G * Cfg::SUB_STRIDE, idx1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * 512 + (my_row + 4 * i) * 4;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx0[i]) : "r"(entry) : "memory");
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx1[i]) : "r"(entry + G * 512) : "memory");
-                    if (4 * i >= rows_left || !ok0)
+                    if (i >= rows_left || !ok0)
                         idx0[i] = -1;
-                    if (4 * i >= rows_left || !ok1)
+                    if (i >= rows_left || !ok1)
                         idx1[i] = -1;
                 }
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                 const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
-                gather_rows(stage, swz0, swz1, xq + (CIN >= 64 ? (blk % CB) * 64 : 0), CIN, idx0);
-                gather_rows(stage + WG_BLOCK_BYTES, swz0, swz1, xq + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), CIN, idx1);
+                gather_rows(stage, q, xq + (CIN >= 64 ? (blk % CB) * 64 : 0), CIN, idx0);
+                gather_rows(stage + WG_BLOCK_BYTES, q, xq + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), CIN, idx1);
                 __syncwarp();
                 if (lane == 0)
                     mbar_arrive(bar_iempty + 8 * e);
@@ -294,7 +299,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     for (int sb = 0; sb < G; ++sb) {
                         const int tap = first_tap(blk + h) + sb;
                         if (blk + h < total_blocks && tap < k3)
-                            cp_async16(smem_idx + e * Cfg::RING_BYTES + (h * G + sb) * 512 + lane * 16,
+                            cp_async16(smem_idx + e * Cfg::RING_BYTES + (h * G + sb) * Cfg::SUB_STRIDE + lane * 16,
                                        lane_nbr + int64_t(tap) * pitch + tile * WG_TILE, 16u);
                     }
                 cp_async_arrive_noinc(bar_ifull + 8 * e);

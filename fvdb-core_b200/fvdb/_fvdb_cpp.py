@@ -438,7 +438,7 @@ def _run_conv(x: torch.Tensor, w_packed: torch.Tensor, nbr: torch.Tensor, n_in: 
     if n_out == 0:
         return y
     code = _DTYPE_CODE[dtype]
-    scratch_bytes = int(lib.fvc_conv_scratch_bytes(n_out, cin, cout, k3, code))
+    scratch_bytes = int(lib.fvc_conv_scratch_bytes(n_in, n_out, cin, cout, k3, code))
     scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
     check(
         lib.fvc_conv_forward(

@@ -10,7 +10,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "libfvdbconv.so"
 
 FVC_OK, FVC_ERR_VALUE, FVC_ERR_RUNTIME, FVC_ERR_INDEX, FVC_ERR_CUDA, FVC_ERR_UNSUPPORTED = range(6)
 FVC_F16, FVC_BF16, FVC_F32, FVC_F64 = range(4)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class FvcGridBatch(C.Structure):
@@ -58,7 +58,7 @@ SIGNATURES = {
     "fvc_neighbor_indexes": (C.c_int, [_GB, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "fvc_ijk_to_index": (C.c_int, [_GB, _vp, _vp, _i64, _i32, _vp, _vp]),
     "fvc_pack_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "fvc_conv_scratch_bytes": (_sz, [_i64, _i32, _i32, _i64, _i32]),
+    "fvc_conv_scratch_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64, _i32]),
     "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
     "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64, _i32]),
     "fvc_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),

@@ -35,13 +35,26 @@ class HostPipelinedConv:
         per = max(1, (tiles + num_chunks - 1) // num_chunks)
         self.bounds = [(t * 128, min((t + per) * 128, n)) for t in range(0, tiles, per)]
         self.s_in, self.s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        # upload dependencies, read off the map itself: chunk c may start once the chunk holding the largest row it
+        # gathers has landed (neighbours never leave the grid, but a grid can span any number of chunks)
+        self.fwd_needs = self._last_chunk_needed(self.topo._out_map())
+        self.bwd_needs = self._last_chunk_needed(self.topo._in_map())
+
+    def _last_chunk_needed(self, nbr: torch.Tensor) -> list[int]:
+        tops = torch.stack([nbr[:, r0:r1].amax() for r0, r1 in self.bounds]).tolist()  # one sync, at construction
+        starts = [r0 for r0, _ in self.bounds]
+        needs = []
+        for c, top in enumerate(tops):
+            holder = max(i for i, r0 in enumerate(starts) if r0 <= max(int(top), 0))
+            needs.append(max(c, holder))
+        return needs
 
     # ---- one sub-range call of the output-stationary kernel --------------------------------------
     def _conv_rows(self, x, w_packed, nbr, mask, r0, r1, cin, cout, out):
         code = cpp._DTYPE_CODE[x.dtype]
         k3, pitch = int(nbr.shape[0]), int(nbr.stride(0))
         words = (k3 + 63) // 64
-        scratch_bytes = int(lib.fvc_conv_scratch_bytes(r1 - r0, cin, cout, k3, code))
+        scratch_bytes = int(lib.fvc_conv_scratch_bytes(int(x.shape[0]), r1 - r0, cin, cout, k3, code))
         scratch = torch.empty(max(scratch_bytes, 16), dtype=torch.uint8, device=x.device)
         check(
             lib.fvc_conv_forward(
@@ -95,9 +108,8 @@ class HostPipelinedConv:
                 dy[r0:r1].copy_(dy_host[r0:r1], non_blocking=True)
                 dy_ready.append(torch.cuda.Event())
                 dy_ready[-1].record(self.s_in)
-        last = len(self.bounds) - 1
-        for c, (r0, r1) in enumerate(self.bounds):  # forward: a chunk may gather rows of the next chunk's leading grid
-            main.wait_event(x_ready[min(c + 1, last)])
+        for c, (r0, r1) in enumerate(self.bounds):  # forward
+            main.wait_event(x_ready[self.fwd_needs[c]])
             self._conv_rows(x, w_fwd, out_map, out_mask, r0, r1, cin, cout, y)
             done = torch.cuda.Event()
             done.record(main)
@@ -105,7 +117,7 @@ class HostPipelinedConv:
                 self.s_out.wait_event(done)
                 y_host[r0:r1].copy_(y[r0:r1], non_blocking=True)
         for c, (r0, r1) in enumerate(self.bounds):  # backward
-            main.wait_event(dy_ready[min(c + 1, last)])
+            main.wait_event(dy_ready[self.bwd_needs[c]])
             self._conv_rows(dy, w_bwd, in_map, in_mask, r0, r1, cout, cin, gx)
             gw_chunk = torch.empty(tuple(weights.shape), dtype=dtype, device=dev)
             self._wgrad_rows(x, dy, r0, r1, cin, cout, gw_chunk)

@@ -106,41 +106,52 @@ def random_occupancy(bbox: int = 292, pct: float = 20.0, seed: int = 42, device=
     return torch.stack([idx // (bbox * bbox), (idx // bbox) % bbox, idx % bbox], dim=1).to(torch.int32)
 
 
-def lidar_sweep(target: int = 1_000_000, seed: int = 0, device="cpu", voxel: float = 0.1, max_range: float = 80.0) -> torch.Tensor:
+def lidar_sweep(target: int = 1_000_000, seed: int = 0, device="cpu", voxel: float = 0.1, max_range: float = 80.0, max_sweeps: int = 256) -> torch.Tensor:
     """C4: accumulated 64-beam spinning-LiDAR sweeps (elevation -25..+3 deg, 0.1 deg azimuth) against a ground
-    plane and 30-60 random boxes, with per-sweep pose jitter, voxelised at ``voxel`` m; sweeps are accumulated
-    until ``target`` unique voxels are reached."""
+    plane and 30-60 random boxes, voxelised at ``voxel`` m.  The sensor drives along a random heading (1.5 m
+    per revolution, with pose jitter); sweeps are accumulated until ``target`` unique voxels are reached.  Scene
+    parameters come from a CPU generator (deterministic per seed); the ray casting is vectorised over
+    rays x boxes on ``device``."""
     g = _gen(seed, "cpu")
     n_boxes = int(torch.randint(30, 61, (1,), generator=g))
     centres = (torch.rand((n_boxes, 2), generator=g) - 0.5) * 2 * (max_range * 0.8)
     half = torch.rand((n_boxes, 3), generator=g) * torch.tensor([4.0, 4.0, 3.0]) + torch.tensor([1.0, 1.0, 1.0])
+    lo = torch.cat([centres - half[:, :2], torch.zeros(n_boxes, 1)], dim=1).to(device)          # boxes sit on the ground
+    hi = torch.cat([centres + half[:, :2], 2 * half[:, 2:3]], dim=1).to(device)
     elev = torch.deg2rad(torch.linspace(-25.0, 3.0, 64))
     azim = torch.deg2rad(torch.arange(0.0, 360.0, 0.1))
     el, az = torch.meshgrid(elev, azim, indexing="ij")
-    dirs = torch.stack([torch.cos(el) * torch.cos(az), torch.cos(el) * torch.sin(az), torch.sin(el)], dim=-1).reshape(-1, 3)
+    dirs = torch.stack([torch.cos(el) * torch.cos(az), torch.cos(el) * torch.sin(az), torch.sin(el)], dim=-1).reshape(-1, 3).to(device)
+    heading = float(torch.rand(1, generator=g)) * 2 * math.pi
+    start = (torch.rand(2, generator=g) - 0.5) * 20.0
+    jitter = (torch.rand((max_sweeps, 3), generator=g) - 0.5)                                   # xy jitter (m) and yaw
     sensor_h = 1.8
-    seen = None
-    for sweep in range(64):
-        pose = torch.cat([(torch.rand(2, generator=g) - 0.5) * 20.0, torch.tensor([sensor_h])])
-        yaw = float(torch.rand(1, generator=g)) * 2 * math.pi
-        rot = torch.tensor([[math.cos(yaw), -math.sin(yaw), 0.0], [math.sin(yaw), math.cos(yaw), 0.0], [0.0, 0.0, 1.0]])
+    # voxel key: 3 x 21-bit biased coordinates in one int64, so accumulation is a 1-D unique
+    bias = 1 << 20
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    for sweep in range(max_sweeps):
+        along = 1.5 * sweep
+        pose = torch.tensor([float(start[0]) + along * math.cos(heading) + float(jitter[sweep, 0]),
+                             float(start[1]) + along * math.sin(heading) + float(jitter[sweep, 1]), sensor_h], device=device)
+        yaw = heading + 0.2 * float(jitter[sweep, 2])
+        rot = torch.tensor([[math.cos(yaw), -math.sin(yaw), 0.0], [math.sin(yaw), math.cos(yaw), 0.0], [0.0, 0.0, 1.0]], device=device)
         d = dirs @ rot.T
-        t_hit = torch.full((d.shape[0],), float("inf"))
-        down = d[:, 2] < -1e-6
-        t_hit[down] = -pose[2] / d[down, 2]  # ground plane z = 0
-        for b in range(n_boxes):  # slab test against each box (box sits on the ground)
-            lo = torch.tensor([centres[b, 0] - half[b, 0], centres[b, 1] - half[b, 1], 0.0])
-            hi = torch.tensor([centres[b, 0] + half[b, 0], centres[b, 1] + half[b, 1], 2 * half[b, 2]])
-            inv = 1.0 / torch.where(d.abs() < 1e-9, torch.full_like(d, 1e-9), d)
-            t0, t1 = (lo - pose) * inv, (hi - pose) * inv
-            tmin = torch.minimum(t0, t1).max(dim=1).values
-            tmax = torch.maximum(t0, t1).min(dim=1).values
-            ok = (tmax >= tmin) & (tmin > 0)
-            t_hit = torch.where(ok & (tmin < t_hit), tmin, t_hit)
-        ok = torch.isfinite(t_hit) & (t_hit <= max_range)
+        t_hit = torch.where(d[:, 2] < -1e-6, -sensor_h / d[:, 2].clamp(max=-1e-6), torch.full_like(d[:, 2], float("inf")))  # ground z = 0
+        inv = 1.0 / torch.where(d.abs() < 1e-9, torch.full_like(d, 1e-9), d)
+        for b0 in range(0, n_boxes, 16):  # slab test, 16 boxes at a time: [rays, 16, 3]
+            t0 = (lo[b0:b0 + 16] - pose)[None] * inv[:, None]
+            t1 = (hi[b0:b0 + 16] - pose)[None] * inv[:, None]
+            tmin = torch.minimum(t0, t1).max(dim=2).values
+            tmax = torch.maximum(t0, t1).min(dim=2).values
+            tbox = torch.where((tmax >= tmin) & (tmin > 0), tmin, torch.full_like(tmin, float("inf"))).min(dim=1).values
+            t_hit = torch.minimum(t_hit, tbox)
+        ok = t_hit <= max_range
         pts = pose + d[ok] * t_hit[ok, None]
-        ijk = _unique_rows(torch.floor(pts / voxel).to(torch.int32))
-        seen = ijk if seen is None else _unique_rows(torch.cat([seen, ijk]))
-        if seen.shape[0] >= target:
+        ijk = torch.floor(pts / voxel).to(torch.int64) + bias
+        keys = torch.unique(torch.cat([keys, (ijk[:, 0] << 42) | (ijk[:, 1] << 21) | ijk[:, 2]]))
+        if keys.numel() >= target:
             break
-    return seen[torch.randperm(seen.shape[0], generator=g)[:target]].contiguous().to(device) if seen.shape[0] > target * 1.05 else seen.to(device)
+    if keys.numel() > target * 1.05:
+        keep = torch.randperm(keys.numel(), generator=g)[:target].to(device)
+        keys = keys[keep.sort().values]
+    return torch.stack([(keys >> 42) - bias, ((keys >> 21) & ((1 << 21) - 1)) - bias, (keys & ((1 << 21) - 1)) - bias], dim=1).to(torch.int32).contiguous()

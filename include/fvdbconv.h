@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FVC_ABI_VERSION 1
+#define FVC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FVC_API __attribute__((visibility("default")))
@@ -197,11 +197,14 @@ FVC_API int fvc_pack_weights(const void *weights, const int64_t strides[5], int3
  * map, w packed with layout 1): the maps are already oriented (GatherScatterDefault.cu:734-740).
  * x, y, w share `dtype`; accumulation is fp32 (fp64 for FVC_F64).  y is fully overwritten (rows with
  * no neighbour become 0; GatherScatterDefault.cu:696).  bias (may be NULL): [Cout] in `dtype`, added in
- * the epilogue (fvdb/nn/modules.py:370-371).  path: 0 = automatic (tensor-core kernel when dtype is
- * f16/bf16 and the channel counts allow it, else the CUDA-core kernel), 1 = force CUDA-core path,
- * 2 = force tensor-core path (FVC_ERR_UNSUPPORTED if not admissible).  tile_mask: fvc_kmap_tile_mask of `nbr`
- * (may be NULL: no unit skipping). */
-FVC_API size_t fvc_conv_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype);
+ * the epilogue (fvdb/nn/modules.py:370-371).  path: 0 = automatic (tensor-core kernel when the dtype is
+ * f16/bf16/f32 and the channel counts allow it, else the CUDA-core kernel), 1 = force CUDA-core path,
+ * 2 = force tensor-core path (FVC_ERR_UNSUPPORTED if not admissible).  fp32 runs on the tensor pipe as a
+ * three-way bf16 split (six exact bf16 products per fp32 product, fp32 accumulate; relative error ~1e-6,
+ * inside the reference's 1e-5 bar); the CUDA-core path is plain fp32 FMA.  tile_mask: fvc_kmap_tile_mask of
+ * `nbr` (may be NULL: no unit skipping).  scratch: 256-byte aligned, fvc_conv_scratch_bytes() bytes (weight
+ * image + for fp32 the split copy of the n_in feature rows); 0 bytes when only the CUDA-core path applies. */
+FVC_API size_t fvc_conv_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype);
 FVC_API int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
                      const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                      int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream);

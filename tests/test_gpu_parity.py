@@ -392,6 +392,58 @@ def test_tensor_core_identity_map_is_plain_gemm(fvdb, cin, cout):
     assert _rel_err(y, want.cpu()) <= 1e-2
     torch.testing.assert_close(y.float(), want, rtol=2e-2, atol=2e-2)
 
+@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 32), (16, 16), (128, 128), (16, 64), (256, 32)])
+def test_fp32_tensor_core_split_identity_map_is_fp32_gemm(fvdb, cin, cout):
+    # fp32 on the tensor pipe = three-way bf16 split (six exact products, two TMEM accumulators): on an identity map the
+    # result must be the fp32 GEMM to ~1e-6, far inside the reference's 1e-5 bar and ~1000x tighter than one bf16 pass.
+    cpp = fvdb._fvdb_cpp
+    coords = _random_batch(12, n=900, extent=7, batches=1, dup=False)[0]
+    a, b = _grid(fvdb, [coords]), _grid(fvdb, [coords])
+    topo = cpp.gs_build_topology(a.data, b.data, [1, 1, 1], [1, 1, 1])
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn((a.total_voxels, cin), generator=gen).to(DEV)
+    w = (torch.randn((cout, cin, 1, 1, 1), generator=gen) / cin**0.5).to(DEV)
+    bias = torch.randn(cout, generator=gen).to(DEV)
+    try:
+        cpp.set_conv_path("tc")
+        y = cpp.gs_conv(x, w, topo)
+        yb = cpp.gs_conv(x, w, topo, bias)
+    finally:
+        cpp.set_conv_path("auto")
+    want = (x.double() @ w[:, :, 0, 0, 0].double().T).float().cpu()
+    assert y.dtype == torch.float32 and _rel_err(y, want) <= 2e-6
+    torch.testing.assert_close(yb.cpu(), want + bias.cpu(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("positive", [False, True])
+def test_fp32_tensor_core_split_matches_cuda_core_path(fvdb, positive):
+    # Same plan through both kernel families; same-sign data is the worst case for the tensor pipe's truncating
+    # accumulation (every step loses up to one ulp in the same direction).
+    from fvdb.utils.synthetic import sphere_shell
+
+    cpp = fvdb._fvdb_cpp
+    grid = _grid(fvdb, [sphere_shell(target=9000, domain=64, seed=7, device="cpu").numpy(), _random_batch(8, n=3000, extent=9, batches=1)[0]])
+    plan = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid, grid)
+    topo = plan._backend.topology
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn((grid.total_voxels, 64), generator=gen)
+    w = torch.randn((64, 64, 3, 3, 3), generator=gen) / 41.0
+    dy = torch.randn((grid.total_voxels, 64), generator=gen)
+    if positive:
+        x, w, dy = x.abs(), w.abs(), dy.abs()
+    x, w, dy = x.to(DEV), w.to(DEV), dy.to(DEV)
+    got = {}
+    for path in ("simt", "auto"):
+        try:
+            cpp.set_conv_path(path)
+            got[path] = (cpp.gs_conv(x, w, topo), *cpp.gs_conv_backward(dy, x, w, topo))
+        finally:
+            cpp.set_conv_path("auto")
+    for a, b in zip(got["simt"], got["auto"]):
+        assert _rel_err(b, a.cpu()) <= 5e-6
+    want_y, want_gx, want_gw = _oracle_run(topo, x, w, dy)
+    assert _rel_err(got["auto"][0], want_y) <= 1e-5 and _rel_err(got["auto"][1], want_gx) <= 1e-5
+
 
 def test_pred_gather_igemm_backend_admission_and_values(fvdb):
     # reference: backend='pred_gather_igemm' (forward-only SM80 TF32 kernel, tests/unit/test_conv_pred_gather_igemm.py);
