@@ -39,6 +39,7 @@ CONFIGS = {
     "c1": dict(gen="sphere_shell", grids=1, voxels=100_000, kernel=3, cin=32, cout=32, dtype="f32", desc="C1 single grid ~100k voxels, 3^3 32->32 fp32"),
     "c2": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=64, cout=64, dtype="bf16", desc="C2 ScanNet-shaped 8 grids x ~200k voxels, 3^3 64->64 bf16 fwd+bwd"),
     "c3": dict(gen="indoor_room", grids=16, voxels=150_000, kernel=3, cin=32, cout=32, dtype="bf16", desc="C3 sparse UNet block stack (3^3 convs, 2^3 s2 down, transposed up, 32..256 ch) on 16 indoor grids, training step"),
+    "c2f32": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=64, cout=64, dtype="f32", desc="C2-shaped 8 grids x ~200k voxels, 3^3 64->64 fp32 fwd+bwd (three-way bf16 split on the tensor pipe)"),
     "c2x128": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C2-shaped 8 grids x ~200k voxels, 3^3 128->128 bf16 fwd+bwd"),
     "c4": dict(gen="lidar_sweep", grids=32, voxels=1_000_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C4 KITTI-shaped 32 grids x ~1M voxels, 3^3 128->128 bf16"),
     "c5": dict(gen="random_occupancy", grids=8, voxels=4_979_000, kernel=5, cin=16, cout=16, dtype="bf16", desc="C5 8 grids x ~5M voxels, 5^3 16->16"),

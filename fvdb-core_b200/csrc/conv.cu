@@ -44,10 +44,10 @@ int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void
     return simt_forward(a);
 }
 
-size_t fvc_conv_wgrad_scratch_bytes(int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout, int64_t kernel_volume,
+size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout, int64_t kernel_volume,
                                     int32_t dtype) {
     size_t simt = simt_wgrad_scratch_bytes(total_pairs, cin, cout, kernel_volume, dtype);
-    size_t tc = tc_wgrad_supported(cin, cout, kernel_volume, dtype) ? tc_wgrad_scratch_bytes(n_out, cin, cout, kernel_volume, dtype) : 0;
+    size_t tc = tc_wgrad_supported(cin, cout, kernel_volume, dtype) ? tc_wgrad_scratch_bytes(n_in, n_out, cin, cout, kernel_volume, dtype) : 0;
     return simt > tc ? simt : tc;
 }
 

@@ -52,7 +52,7 @@ bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
 size_t tc_forward_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
 int tc_forward(const ConvArgs &a);
 bool tc_wgrad_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
-size_t tc_wgrad_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
+size_t tc_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
 int tc_wgrad(const WgradArgs &a);
 
 } // namespace fvc

@@ -290,20 +290,24 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
 
     if (warp < PW) {
         // ================= gather producers: warp w copies rows [RPW*w, RPW*(w+1)) =================
-        // lane = (g, q): 8 lanes q cover one 128-byte row (one full line); lane group g owns the NI CONSECUTIVE rows
-        // row0 .. row0 + NI - 1, so its map entries are NI contiguous int32 (128-bit shared loads) and instruction i
-        // of the warp copies rows {row0(g) + i}.
+        // lane = (lg, q): 8 lanes q cover one 128-byte row (one full line).  With one tap per row (Cin >= 64) lane group
+        // lg takes rows lg, lg + 4, ... (an instruction copies 4 consecutive output rows, whose neighbours tend to be
+        // consecutive feature rows).  With packed taps (Cin < 64) it takes NI CONSECUTIVE rows instead, so that its map
+        // entries are contiguous (128-bit shared loads, no bank conflicts between the taps a quarter-warp reads).
         constexpr int RPW = TC_TILE_M / PW, NI = RPW / 4;
+        constexpr bool SEQ = G > 1;
         const int q = lane & 7;
-        const int row0 = warp * RPW + (lane >> 3) * NI;
-        // lane q copies 16-byte chunk q of each of its rows; with packed taps (Cin < 64) that chunk belongs to tap
-        // `sub` of the group and to channel chunk q % CPT of that tap's feature row
+        const int row0 = warp * RPW + (lane >> 3) * (SEQ ? NI : 1); // rows row0 + i * (SEQ ? 1 : 4), i < NI
+        // lane q copies 16-byte chunk q of each of its rows; with packed taps that chunk belongs to tap `sub` of the
+        // group and to channel chunk q % CPT of that tap's feature row
         const int sub = q / CPT;
         const uint16_t *xq = x + (CIN >= 64 ? q * 8 : (q % CPT) * 8);
         uint32_t dst_off[NI]; // row offset + swizzled chunk position inside a stage
 #pragma unroll
-        for (int i = 0; i < NI; ++i)
-            dst_off[i] = uint32_t(row0 + i) * 128u + (uint32_t(q ^ ((row0 + i) & 7)) << 4);
+        for (int i = 0; i < NI; ++i) {
+            const int r = row0 + i * (SEQ ? 1 : 4);
+            dst_off[i] = uint32_t(r) * 128u + (uint32_t(q ^ (r & 7)) << 4);
+        }
         const uint32_t idx_src = smem_idx + sub * Cfg::SUB_STRIDE + row0 * 4;
         int s = 0;
         uint32_t ph = 0;
@@ -313,20 +317,26 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             const int e = u & (TC_IDX_RING - 1);
             mbar_wait(bar_ifull + 8 * e, (u / TC_IDX_RING) & 1);
             int idx[NI];
+            if (SEQ) {
 #pragma unroll
-            for (int i = 0; i < NI; i += 4)
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(idx[i]), "=r"(idx[i + 1]), "=r"(idx[i + 2]), "=r"(idx[i + 3])
-                             : "r"(idx_src + e * Cfg::RING_BYTES + i * 4)
-                             : "memory");
-            // row row0 + i exists iff i < rows_left; a tap beyond the kernel volume (last, partial group) is empty
+                for (int i = 0; i < NI; i += 4)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(idx[i]), "=r"(idx[i + 1]), "=r"(idx[i + 2]), "=r"(idx[i + 3])
+                                 : "r"(idx_src + e * Cfg::RING_BYTES + i * 4)
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int i = 0; i < NI; ++i)
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(idx[i]) : "r"(idx_src + e * Cfg::RING_BYTES + i * 16) : "memory");
+            }
+            // row row0 + i * step exists iff i * step < rows_left; a tap beyond the kernel volume (last, partial group) is empty
             const int64_t rows_left = (G == 1 || g * G + sub < k3) ? n_out - (tile0 + t) * TC_TILE_M - row0 : 0;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             const uint32_t dst = smem_a + s * TC_A_BYTES;
             const uint16_t *xj = xq + j * 64 + (SPLIT ? int((unit >> 3) & 3u) * CIN : 0);
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                const bool ok = idx[i] >= 0 && i < rows_left;
+                const bool ok = idx[i] >= 0 && i * (SEQ ? 1 : 4) < rows_left;
                 cp_async16(dst + dst_off[i], ok ? xj + int64_t(idx[i]) * XS : x, ok ? 16u : 0u);
             }
             __syncwarp();
@@ -556,6 +566,15 @@ size_t tc_forward_scratch_bytes(int64_t n_in, int64_t, int32_t cin, int32_t cout
     return tc_image_bytes(cin, cout, k3, 1) + 256;
 }
 
+int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t stream) {
+    const int64_t work = n * (c / 8);
+    if (work <= 0)
+        return FVC_OK;
+    tc_split_rows_kernel<<<int(ceil_div(work, 256) > 148 * 16 ? 148 * 16 : ceil_div(work, 256)), 256, 0, stream>>>(x, n, c, xs);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
 static int tc_forward_split(const ConvArgs &a) {
     uint8_t *img = reinterpret_cast<uint8_t *>(a.scratch);
     uint16_t *xs = reinterpret_cast<uint16_t *>(img + tc_image_bytes(a.cin, a.cout, a.k3, 3));
@@ -563,12 +582,9 @@ static int tc_forward_split(const ConvArgs &a) {
     tc_pack_b_split_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
         reinterpret_cast<const float *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
     FVC_LAUNCH_CHECK();
-    const int64_t work = a.n_in * (a.cin / 8);
-    if (work > 0) {
-        tc_split_rows_kernel<<<int(ceil_div(work, 256) > 148 * 16 ? 148 * 16 : ceil_div(work, 256)), 256, 0, a.stream>>>(
-            reinterpret_cast<const float *>(a.x), a.n_in, a.cin, xs);
-        FVC_LAUNCH_CHECK();
-    }
+    const int rc = tc_split_rows(reinterpret_cast<const float *>(a.x), a.n_in, a.cin, xs, a.stream);
+    if (rc)
+        return rc;
 #define FVC_TCS_CASE(CI, CO, T, S, B) \
     if (a.cin == CI && a.cout == CO)  \
         return launch_tc_fwd<CI, CO, T, S, B, 4, true>(a, xs, img);

@@ -1,4 +1,5 @@
-// conv_tc_wgrad.cu -- tcgen05 / TMEM weight gradient for f16 / bf16 (fp32 accumulate, fixed-order reduction).
+// conv_tc_wgrad.cu -- tcgen05 / TMEM weight gradient for f16 / bf16 and (three-way bf16 split) fp32: fp32 accumulate,
+// fixed-order reduction.
 //
 //   dW[k][ci][co] = sum over output rows o of  X[nbr[k][o]][ci] * dY[o][co]        (GatherScatterDefault.cu:806-807)
 //
@@ -12,6 +13,11 @@
 // the CTA streams over its share of the row tiles.  TMEM (512 columns) holds 512 / Cout units, so the
 // taps are split into groups (grid.y) and the rows into chunks (grid.x); every CTA writes one fp32 partial
 // [K^3][Cin][Cout] slice that wgrad_reduce_partials sums in a fixed order (deterministic, no atomics).
+//
+// fp32 (SPLIT = true): X and dY arrive as bf16 split rows [N][3][C] (conv_tc.cu: tc_split_rows); per (unit, X split i) the
+// issuer runs the MMAs against dY splits 0 .. 2 - i, x0.d0 into the unit's main accumulator, the five small terms into a
+// second one.  tcgen05 truncates on every accumulate, so the full-magnitude chain is kept short: every `seg_tiles` row
+// tiles the CTA drains its accumulators and adds them (rounded fp32 adds, same CTA, fixed order) into its partial slice.
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
 
@@ -27,23 +33,28 @@ constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 reduction-side el
 
 // Small channel counts are packed like in the forward kernel: an A block holds G = 64 / CIN taps x CIN channels;
 // a dY row narrower than 64 channels is zero-padded to one 128-byte row (N = 64 for the MMA, extra columns unused).
-template <int CIN, int COUT, int STAGES> struct TcWgradCfg {
+template <int CIN, int COUT, int STAGES, bool SPLIT = false> struct TcWgradCfg {
     static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per A block
     static constexpr int CB = CIN >= 64 ? CIN / 64 : 1;     // A channel blocks per tap (group)
     static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a row
     static constexpr int NB = COUT >= 64 ? COUT / 64 : 1;   // B blocks
     static constexpr int NPAD = COUT >= 64 ? COUT : 64;     // MMA N = TMEM columns per unit
     static constexpr int BQ = COUT >= 64 ? 8 : COUT / 8;    // valid 16-byte chunks of a dY row per B block
-    static constexpr int MAX_UNITS = 512 / NPAD;            // accumulators that fit TMEM
+    static constexpr int NS = SPLIT ? 3 : 1;                // bf16 splits per fp32 operand
+    static constexpr int XS = NS * CIN, YS = NS * COUT;     // row strides (elements) of the (split) feature / grad rows
+    static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * NPAD; // TMEM columns per unit (SPLIT: main | small-term accumulator)
+    static constexpr int MAX_UNITS = 512 / ACC_COLS;        // accumulators that fit TMEM
+    static constexpr int BSTAGES = (SPLIT && COUT >= 128) ? 1 : 2;
     static constexpr int RING = G == 4 ? 4 : 8;             // kernel-map ring depth
     static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;    // 128 int32 per tap (+ a 16-byte pad so packed taps sit on different banks)
     static constexpr int RING_BYTES = 2 * G * SUB_STRIDE;   // two blocks x G taps
     static constexpr int A_STAGE = 2 * WG_BLOCK_BYTES;
-    static constexpr int B_STAGE = NB * WG_BLOCK_BYTES;
+    static constexpr int B_STAGE = NS * NB * WG_BLOCK_BYTES; // [split][64-channel block] of one dY tile
     static constexpr int NUM_BARS = 2 * STAGES + 5 + 2 * RING;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + 2 * size_t(B_STAGE) + size_t(RING) * RING_BYTES + 8 * NUM_BARS + 16;
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * A_STAGE + size_t(BSTAGES) * B_STAGE + size_t(RING) * RING_BYTES + 8 * NUM_BARS + 16;
     static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128 || CIN == 256, "unsupported Cin");
     static_assert(COUT == 16 || COUT == 32 || COUT == 64 || COUT == 128 || COUT == 256, "unsupported Cout");
+    static_assert(!SPLIT || COUT <= 128, "fp32 split: Cout <= 128");
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -63,25 +74,26 @@ __device__ __forceinline__ void lds_v4x2(uint32_t addr, int (&v)[8]) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr + 16) : "memory");
 }
 
-template <int CIN, int COUT, int STAGES>
+template <int CIN, int COUT, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
                      int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
-                     int tiles_per_chunk, uint32_t idesc, float *__restrict__ partial) {
-    using Cfg = TcWgradCfg<CIN, COUT, STAGES>;
+                     int tiles_per_chunk, int seg_tiles, uint32_t idesc, float *__restrict__ partial) {
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT>;
     constexpr int G = Cfg::G, CB = Cfg::CB, CPT = Cfg::CPT, NB = Cfg::NB, NPAD = Cfg::NPAD, RING = Cfg::RING;
+    constexpr int NS = Cfg::NS, XS = Cfg::XS, YS = Cfg::YS, ACC = Cfg::ACC_COLS, BSTAGES = Cfg::BSTAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * Cfg::A_STAGE;
-    const uint32_t smem_idx = smem_b + 2 * Cfg::B_STAGE;
+    const uint32_t smem_idx = smem_b + BSTAGES * Cfg::B_STAGE;
     const uint32_t bars = smem_idx + RING * Cfg::RING_BYTES;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 16;
     const uint32_t bar_accum = bar_bempty + 16;
     const uint32_t bar_ifull = bar_accum + 8, bar_iempty = bar_ifull + 8 * RING;
     const uint32_t tmem_slot = bar_iempty + 8 * RING;
-    __shared__ uint32_t s_started; // units whose accumulator was written at least once (MMA thread -> epilogue)
+    __shared__ uint32_t s_started[2]; // per segment parity: units whose accumulator was written (MMA thread -> drain)
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (smem_base - smem_u32(smem_raw)) + (tmem_slot - smem_base));
 
@@ -127,7 +139,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     };
 
     if (threadIdx.x == 0) {
-        s_started = 0u;
+        s_started[0] = s_started[1] = 0u;
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, WG_PW * 32);
             mbar_init(bar_empty + 8 * s, 1);
@@ -151,100 +163,134 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp < WG_PW) {
-        // ================= producers: dY tile, then the gathered X blocks of every live unit =================
+        // ================= producers: dY tile, then the gathered X blocks of every live unit; drain per segment =================
         const int q = lane & 7, sub = q / CPT;
         const int row0 = warp * 32 + (lane >> 3) * 8; // rows row0 + i, i < 8
         const uint32_t dst0 = uint32_t(row0) * 128u;
         const uint16_t *xq = x + (CIN >= 64 ? q * 8 : (q % CPT) * 8), *dyq = dy + q * 8;
-        int s = 0, e = 0, tb = 0;
+        // drain role of this warp: TMEM lanes 32w .. 32w+31 = reduction-side element kk of A block `half` of every unit
+        const int half = warp >> 1;
+        const int kk = (warp & 1) * 32 + lane;
+        float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
+        int s = 0, e = 0, tb = 0, seg = 0, seg_t = 0;
         uint32_t ph = 0, eph = 0;
         for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
             const int64_t rows_left = n_out - tile * WG_TILE - row0; // row row0 + i exists iff i < rows_left
             const uint32_t live = live_units(tile);
-            { // B: plain rows of dY (identity "map"); lanes beyond a narrow row's chunks zero-fill
-                const int bs = tb & 1;
-                mbar_wait(bar_bempty + 8 * bs, ((tb >> 1) & 1) ^ 1);
+            { // B: plain rows of dY (identity "map"), every split; lanes beyond a narrow row's chunks zero-fill
+                const int bs = tb % BSTAGES;
+                mbar_wait(bar_bempty + 8 * bs, ((tb / BSTAGES) & 1) ^ 1);
                 int self[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     self[i] = (i < rows_left && q < Cfg::BQ) ? int(tile * WG_TILE + row0 + i) : -1;
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb)
-                    gather_rows(smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES + dst0, q, dyq + nb * 64, COUT, self);
+                for (int j = 0; j < NS; ++j)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+                        gather_rows(smem_b + bs * Cfg::B_STAGE + (j * NB + nb) * WG_BLOCK_BYTES + dst0, q, dyq + j * COUT + nb * 64, YS, self);
                 cp_async_arrive_noinc(bar_bfull + 8 * bs);
             }
             for (uint32_t rest = live; rest; rest &= rest - 1u) {
                 const int blk = 2 * (unit0 + __ffs(rest) - 1);
-                mbar_wait(bar_ifull + 8 * e, eph);
-                int idx0[8], idx1[8];
                 const bool ok0 = first_tap(blk) + sub < k3;
                 const bool ok1 = blk + 1 < total_blocks && first_tap(blk + 1) + sub < k3; // odd block count: zero dummy
-                const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * Cfg::SUB_STRIDE + row0 * 4;
-                lds_v4x2(entry, idx0);
-                lds_v4x2(entry + G * Cfg::SUB_STRIDE, idx1);
+                for (int i = 0; i < NS; ++i) {
+                    mbar_wait(bar_ifull + 8 * e, eph);
+                    int idx0[8], idx1[8];
+                    const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * Cfg::SUB_STRIDE + row0 * 4;
+                    lds_v4x2(entry, idx0);
+                    lds_v4x2(entry + G * Cfg::SUB_STRIDE, idx1);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i >= rows_left || !ok0)
-                        idx0[i] = -1;
-                    if (i >= rows_left || !ok1)
-                        idx1[i] = -1;
-                }
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
-                gather_rows(stage, q, xq + (CIN >= 64 ? (blk % CB) * 64 : 0), CIN, idx0);
-                gather_rows(stage + WG_BLOCK_BYTES, q, xq + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), CIN, idx1);
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(bar_iempty + 8 * e);
-                cp_async_arrive_noinc(bar_full + 8 * s);
-                if (++s == STAGES) {
-                    s = 0;
-                    ph ^= 1u;
-                }
-                if (++e == RING) {
-                    e = 0;
-                    eph ^= 1u;
+                    for (int r = 0; r < 8; ++r) {
+                        if (r >= rows_left || !ok0)
+                            idx0[r] = -1;
+                        if (r >= rows_left || !ok1)
+                            idx1[r] = -1;
+                    }
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
+                    gather_rows(stage, q, xq + i * CIN + (CIN >= 64 ? (blk % CB) * 64 : 0), XS, idx0);
+                    gather_rows(stage + WG_BLOCK_BYTES, q, xq + i * CIN + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), XS, idx1);
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(bar_iempty + 8 * e);
+                    cp_async_arrive_noinc(bar_full + 8 * s);
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                    if (++e == RING) {
+                        e = 0;
+                        eph ^= 1u;
+                    }
                 }
             }
+            if (++seg_t < seg_tiles && tile + 1 < tile_end)
+                continue;
+            // ---- drain: accumulators -> fp32 partial slice [k][ci][co] (first segment stores, later ones add).  The issuer
+            //      cannot touch TMEM again before every producer thread has arrived on the next stage, i.e. after this.
+            mbar_wait(bar_accum, uint32_t(seg & 1));
+            tc_fence_after();
+            const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started[seg & 1]);
+            constexpr int EC = COUT >= 32 ? 32 : 16; // columns drained per tcgen05.ld
+            for (int ul = 0; ul < nunits; ++ul) {
+                const int blk = 2 * (unit0 + ul) + half;
+                const int tap = CIN >= 64 ? blk / CB : blk * G + kk / CIN;
+                const int ci = CIN >= 64 ? (blk % CB) * 64 + kk : kk % CIN;
+                const bool live_row = blk < total_blocks && tap < k3;
+                const bool touched = (started >> ul) & 1u;
+                if (!touched && seg > 0)
+                    continue; // nothing to add
+#pragma unroll
+                for (int c0 = 0; c0 < COUT; c0 += EC) {
+                    uint32_t acc[32];
+                    if (touched) {
+                        const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * ACC + c0);
+                        if (EC == 32)
+                            tmem_ld_32x32b_x32(taddr, acc);
+                        else
+                            tmem_ld_32x32b_x16(taddr, acc);
+                        if (SPLIT) {
+                            uint32_t small[32];
+                            if (EC == 32)
+                                tmem_ld_32x32b_x32(taddr + NPAD, small);
+                            else
+                                tmem_ld_32x32b_x16(taddr + NPAD, small);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int z = 0; z < EC; ++z)
+                                acc[z] = __float_as_uint(__uint_as_float(acc[z]) + __uint_as_float(small[z]));
+                        } else {
+                            tmem_ld_wait();
+                        }
+                    } else { // no row of this CTA's tiles ever reached these taps
+#pragma unroll
+                        for (int z = 0; z < 32; ++z)
+                            acc[z] = 0u;
+                    }
+                    if (live_row) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(slice + (int64_t(tap) * CIN + ci) * COUT + c0);
+#pragma unroll
+                        for (int v = 0; v < EC / 4; ++v) {
+                            uint4 o = make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+                            if (seg > 0) {
+                                const uint4 old = dst[v];
+                                o.x = __float_as_uint(__uint_as_float(old.x) + __uint_as_float(o.x));
+                                o.y = __float_as_uint(__uint_as_float(old.y) + __uint_as_float(o.y));
+                                o.z = __float_as_uint(__uint_as_float(old.z) + __uint_as_float(o.z));
+                                o.w = __float_as_uint(__uint_as_float(old.w) + __uint_as_float(o.w));
+                            }
+                            dst[v] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            ++seg;
+            seg_t = 0;
         }
         cp_async_wait_all();
-
-        // ================= epilogue: accumulators -> fp32 partial slice [k][ci][co] =================
-        mbar_wait(bar_accum, 0);
-        tc_fence_after();
-        const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started);
-        const int half = warp >> 1;                  // which A block of the unit this warp's TMEM lanes belong to
-        const int kk = (warp & 1) * 32 + lane;       // reduction-side element inside the block
-        float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
-        constexpr int EC = COUT >= 32 ? 32 : 16;     // columns drained per tcgen05.ld
-        for (int ul = 0; ul < nunits; ++ul) {
-            const int blk = 2 * (unit0 + ul) + half;
-            const int tap = CIN >= 64 ? blk / CB : blk * G + kk / CIN;
-            const int ci = CIN >= 64 ? (blk % CB) * 64 + kk : kk % CIN;
-            const bool live = blk < total_blocks && tap < k3;
-#pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += EC) {
-                uint32_t acc[32];
-                if ((started >> ul) & 1u) {
-                    const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(ul * NPAD + c0);
-                    if (EC == 32)
-                        tmem_ld_32x32b_x32(taddr, acc);
-                    else
-                        tmem_ld_32x32b_x16(taddr, acc);
-                    tmem_ld_wait();
-                } else { // no row of this CTA's tiles ever reached these taps
-#pragma unroll
-                    for (int z = 0; z < 32; ++z)
-                        acc[z] = 0u;
-                }
-                if (live) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(slice + (int64_t(tap) * CIN + ci) * COUT + c0);
-#pragma unroll
-                    for (int v = 0; v < EC / 4; ++v)
-                        dst[v] = make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
-                }
-            }
-        }
     } else if (warp == WG_WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
@@ -252,35 +298,49 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             const uint64_t desc_hi = make_smem_desc_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFF00000000ull;
             const uint32_t lbo = uint32_t(WG_BLOCK_BYTES >> 4) << 16;
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | lbo;
-            int s = 0, tb = 0;
-            uint32_t ph = 0, started = 0;
+            int s = 0, tb = 0, seg = 0, seg_t = 0;
+            uint32_t ph = 0, started = 0, started_small = 0;
             for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
-                const int bs = tb & 1;
+                const int bs = tb % BSTAGES;
                 const uint32_t live = live_units(tile);
-                mbar_wait(bar_bfull + 8 * bs, (tb >> 1) & 1);
+                mbar_wait(bar_bfull + 8 * bs, (tb / BSTAGES) & 1);
                 const uint32_t b_lo = b_lo0 + uint32_t(bs) * (Cfg::B_STAGE >> 4);
                 for (uint32_t rest = live; rest; rest &= rest - 1u) {
                     const int ul = __ffs(rest) - 1;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + uint32_t(s) * (Cfg::A_STAGE >> 4);
-                    const uint32_t acc0 = (started >> ul) & 1u;
+                    for (int i = 0; i < NS; ++i) {
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const uint32_t a_lo = a_lo0 + uint32_t(s) * (Cfg::A_STAGE >> 4);
+                        for (int jj = 0; jj + i <= (SPLIT ? 2 : 0); ++jj) { // X split i meets dY splits 0 .. 2 - i
+                            const bool main_term = (i | jj) == 0;
+                            const uint32_t acc0 = ((main_term ? started : started_small) >> ul) & 1u;
+                            const uint32_t d = tmem_base + uint32_t(ul * ACC + (main_term ? 0 : NPAD));
+                            const uint32_t bj = b_lo + uint32_t(jj) * ((NB * WG_BLOCK_BYTES) >> 4);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) // 16 rows (K) per MMA = two 8-row swizzle groups = 2048 B = 128 units
-                        umma_f16(tmem_base + uint32_t(ul * NPAD), desc_hi | (a_lo + 128 * kk), desc_hi | (b_lo + 128 * kk), idesc,
-                                 acc0 | uint32_t(kk != 0));
-                    umma_commit(bar_empty + 8 * s);
-                    started |= 1u << ul;
-                    if (++s == STAGES) {
-                        s = 0;
-                        ph ^= 1u;
+                            for (int kk = 0; kk < 8; ++kk) // 16 rows (K) per MMA = two 8-row swizzle groups = 2048 B = 128 units
+                                umma_f16(d, desc_hi | (a_lo + 128 * kk), desc_hi | (bj + 128 * kk), idesc, acc0 | uint32_t(kk != 0));
+                            if (main_term)
+                                started |= 1u << ul;
+                            else
+                                started_small |= 1u << ul;
+                        }
+                        umma_commit(bar_empty + 8 * s);
+                        if (++s == STAGES) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
                 umma_commit(bar_bempty + 8 * bs);
+                if (++seg_t == seg_tiles || tile + 1 == tile_end) { // segment done: hand the accumulators to the drain
+                    *reinterpret_cast<volatile uint32_t *>(&s_started[seg & 1]) = started;
+                    __threadfence_block();
+                    umma_commit(bar_accum);
+                    started = started_small = 0;
+                    ++seg;
+                    seg_t = 0;
+                }
             }
-            *reinterpret_cast<volatile uint32_t *>(&s_started) = started;
-            __threadfence_block();
-            umma_commit(bar_accum);
         }
         __syncwarp();
     } else {
@@ -292,20 +352,22 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             const uint32_t live = live_units(tile);
             for (uint32_t rest = live; rest; rest &= rest - 1u) {
                 const int blk = 2 * (unit0 + __ffs(rest) - 1);
-                mbar_wait(bar_iempty + 8 * e, eph ^ 1u);
+                for (int i = 0; i < NS; ++i) { // one ring entry per gathered stage (the splits re-read the same entries)
+                    mbar_wait(bar_iempty + 8 * e, eph ^ 1u);
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int sb = 0; sb < G; ++sb) {
-                        const int tap = first_tap(blk + h) + sb;
-                        if (blk + h < total_blocks && tap < k3)
-                            cp_async16(smem_idx + e * Cfg::RING_BYTES + (h * G + sb) * Cfg::SUB_STRIDE + lane * 16,
-                                       lane_nbr + int64_t(tap) * pitch + tile * WG_TILE, 16u);
+                        for (int sb = 0; sb < G; ++sb) {
+                            const int tap = first_tap(blk + h) + sb;
+                            if (blk + h < total_blocks && tap < k3)
+                                cp_async16(smem_idx + e * Cfg::RING_BYTES + (h * G + sb) * Cfg::SUB_STRIDE + lane * 16,
+                                           lane_nbr + int64_t(tap) * pitch + tile * WG_TILE, 16u);
+                        }
+                    cp_async_arrive_noinc(bar_ifull + 8 * e);
+                    if (++e == RING) {
+                        e = 0;
+                        eph ^= 1u;
                     }
-                cp_async_arrive_noinc(bar_ifull + 8 * e);
-                if (++e == RING) {
-                    e = 0;
-                    eph ^= 1u;
                 }
             }
         }
@@ -319,14 +381,16 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
 
 // ---- host side ------------------------------------------------------------------------------------
 struct WgradPlan {
-    int groups, units_per_group, chunks, tiles_per_chunk;
+    int groups, units_per_group, chunks, tiles_per_chunk, seg_tiles;
 };
 
-static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3) {
+constexpr int WG_SPLIT_SEG_TILES = 32; // fp32: drain the accumulators every 32 row tiles (<= 256 full-magnitude MMA steps)
+
+static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split) {
     WgradPlan p;
     const int total_blocks = cin >= 64 ? k3 * (cin / 64) : int(ceil_div(k3, 64 / cin));
     const int total_units = (total_blocks + 1) / 2;
-    const int max_units = 512 / (cout >= 64 ? cout : 64);
+    const int max_units = 512 / ((split ? 2 : 1) * (cout >= 64 ? cout : 64));
     p.groups = int(ceil_div(total_units, max_units));
     p.units_per_group = int(ceil_div(total_units, p.groups)); // balanced groups
     const int64_t tiles = ceil_div(n_out, WG_TILE);
@@ -337,54 +401,97 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3) {
         chunks = tiles;
     p.tiles_per_chunk = int(ceil_div(tiles, chunks));
     p.chunks = int(ceil_div(tiles, p.tiles_per_chunk));
+    p.seg_tiles = split ? WG_SPLIT_SEG_TILES : p.tiles_per_chunk;
     return p;
 }
 
-template <int CIN, int COUT, int STAGES> static int launch_tc_wgrad(const WgradArgs &a) {
-    using Cfg = TcWgradCfg<CIN, COUT, STAGES>;
-    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES>;
+// tc_split_rows_kernel lives in conv_tc.cu
+int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t stream);
+
+template <int CIN, int COUT, int STAGES, bool SPLIT = false>
+static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, float *partial) {
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT>;
+    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT>;
     static bool configured = false;
     if (!configured) {
         FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
         configured = true;
     }
-    const WgradPlan p = plan_wgrad(a.n_out, CIN, COUT, a.k3);
-    const uint32_t idesc = make_idesc_f16(128, Cfg::NPAD, a.dtype == FVC_BF16, true, true);
-    float *partial = reinterpret_cast<float *>(a.scratch);
+    const WgradPlan p = plan_wgrad(a.n_out, CIN, COUT, a.k3, SPLIT);
+    const uint32_t idesc = make_idesc_f16(128, Cfg::NPAD, SPLIT || a.dtype == FVC_BF16, true, true);
     dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
-    kernel<<<grid, WG_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(a.x), reinterpret_cast<const uint16_t *>(a.dy),
-                                                      a.nbr, a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out,
-                                                      a.k3, p.units_per_group, p.tiles_per_chunk, idesc, partial);
+    kernel<<<grid, WG_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<const uint16_t *>(dy), a.nbr,
+                                                      a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out, a.k3,
+                                                      p.units_per_group, p.tiles_per_chunk, p.seg_tiles, idesc, partial);
     FVC_LAUNCH_CHECK();
     return wgrad_reduce_partials(partial, p.chunks, a.cin, a.cout, a.k3, a.dtype, a.grad_w, a.stream);
 }
 
 bool tc_wgrad_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
-    if (dtype != FVC_F16 && dtype != FVC_BF16)
+    const bool split = dtype == FVC_F32;
+    if (dtype != FVC_F16 && dtype != FVC_BF16 && !split)
         return false;
     if (k3 < 1 || k3 > 4096)
         return false;
     auto pow2 = [](int c) { return c == 16 || c == 32 || c == 64 || c == 128 || c == 256; };
-    return pow2(cin) && pow2(cout);
+    return pow2(cin) && pow2(cout) && (!split || cout <= 128);
 }
 
-size_t tc_wgrad_scratch_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t) {
-    const WgradPlan p = plan_wgrad(n_out > 0 ? n_out : 1, cin, cout, int(k3));
-    return size_t(p.chunks) * size_t(k3) * size_t(cin) * size_t(cout) * 4 + 256;
+static inline size_t wg_partial_bytes(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, bool split) {
+    const WgradPlan p = plan_wgrad(n_out > 0 ? n_out : 1, cin, cout, int(k3), split);
+    return align_up(size_t(p.chunks) * size_t(k3) * size_t(cin) * size_t(cout) * 4, 256);
+}
+
+// scratch = [fp32 partial slices | split X rows | split dY rows (fp32 only)]
+size_t tc_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
+    const bool split = dtype == FVC_F32;
+    size_t bytes = wg_partial_bytes(n_out, cin, cout, k3, split) + 256;
+    if (split)
+        bytes += align_up(size_t(n_in > 0 ? n_in : 0) * 3 * size_t(cin) * 2, 256) + align_up(size_t(n_out > 0 ? n_out : 0) * 3 * size_t(cout) * 2, 256);
+    return bytes;
 }
 
 int tc_wgrad(const WgradArgs &a) {
-    const size_t need = tc_wgrad_scratch_bytes(a.n_out, a.cin, a.cout, a.k3, a.dtype);
+    const bool split = a.dtype == FVC_F32;
+    const size_t need = tc_wgrad_scratch_bytes(a.n_in, a.n_out, a.cin, a.cout, a.k3, a.dtype);
     FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core wgrad scratch too small: %zu < %zu",
                 a.scratch_bytes, need);
     FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.nbr) & 15) == 0,
-                FVC_ERR_RUNTIME, "tensor-core wgrad needs 16-byte aligned pointers");
+                    (reinterpret_cast<uintptr_t>(a.scratch) & 255) == 0 && (reinterpret_cast<uintptr_t>(a.nbr) & 15) == 0,
+                FVC_ERR_RUNTIME, "tensor-core wgrad needs 16-byte aligned feature / grad / map pointers and 256-byte aligned scratch");
     FVC_REQUIRE(a.pitch % 4 == 0 && a.pitch >= ceil_div(a.n_out, WG_TILE) * WG_TILE, FVC_ERR_RUNTIME,
                 "tensor-core wgrad needs the map pitch (%lld) to be a multiple of 4 covering whole 128-row tiles", (long long)a.pitch);
+    float *partial = reinterpret_cast<float *>(a.scratch);
+    if (split) {
+        uint8_t *base = reinterpret_cast<uint8_t *>(a.scratch) + wg_partial_bytes(a.n_out, a.cin, a.cout, a.k3, true);
+        uint16_t *xs = reinterpret_cast<uint16_t *>(base);
+        uint16_t *dys = reinterpret_cast<uint16_t *>(base + align_up(size_t(a.n_in) * 3 * size_t(a.cin) * 2, 256));
+        int rc = tc_split_rows(reinterpret_cast<const float *>(a.x), a.n_in, a.cin, xs, a.stream);
+        if (rc)
+            return rc;
+        rc = tc_split_rows(reinterpret_cast<const float *>(a.dy), a.n_out, a.cout, dys, a.stream);
+        if (rc)
+            return rc;
+#define FVC_WGS_CASE(CI, CO, S)      \
+    if (a.cin == CI && a.cout == CO) \
+        return launch_tc_wgrad<CI, CO, S, true>(a, xs, dys, partial);
+#define FVC_WGS_CIN(CI)      \
+    FVC_WGS_CASE(CI, 16, 3)  \
+    FVC_WGS_CASE(CI, 32, 3)  \
+    FVC_WGS_CASE(CI, 64, 3)  \
+    FVC_WGS_CASE(CI, 128, 2)
+        FVC_WGS_CIN(16)
+        FVC_WGS_CIN(32)
+        FVC_WGS_CIN(64)
+        FVC_WGS_CIN(128)
+        FVC_WGS_CIN(256)
+#undef FVC_WGS_CIN
+#undef FVC_WGS_CASE
+        return set_error(FVC_ERR_UNSUPPORTED, "no fp32 tensor-core wgrad kernel for channels %d -> %d", a.cin, a.cout);
+    }
 #define FVC_WG_CASE(CI, CO, S)       \
     if (a.cin == CI && a.cout == CO) \
-        return launch_tc_wgrad<CI, CO, S>(a);
+        return launch_tc_wgrad<CI, CO, S>(a, a.x, a.dy, partial);
 #define FVC_WG_CIN(CI)       \
     FVC_WG_CASE(CI, 16, 4)   \
     FVC_WG_CASE(CI, 32, 4)   \

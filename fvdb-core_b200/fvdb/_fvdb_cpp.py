@@ -492,7 +492,7 @@ def _backward(grad_output, features, weights, topo, name, want_transposed):
             grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3, None, topo._in_mask())
         # wgrad: dW[k] = X[g]^T . dY[s]  (:806-813)
         grad_weights = torch.empty(tuple(weights.shape), dtype=working, device=device)
-        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_out, topo.total_pairs, cin, cout, k3, code))
+        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, topo.total_pairs, cin, cout, k3, code))
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
         offsets_host = topo.offsets
         out_map = topo._out_map()

@@ -60,7 +60,7 @@ SIGNATURES = {
     "fvc_pack_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fvc_conv_scratch_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64, _i32]),
     "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
-    "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64, _i32]),
+    "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i64, _i32]),
     "fvc_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
 }
 

@@ -69,7 +69,7 @@ class HostPipelinedConv:
         nbr, mask = topo._out_map(), topo._out_mask()
         k3, pitch = int(nbr.shape[0]), int(nbr.stride(0))
         words = (k3 + 63) // 64
-        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(r1 - r0, topo.total_pairs, cin, cout, k3, code))
+        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(int(x.shape[0]), r1 - r0, topo.total_pairs, cin, cout, k3, code))
         scratch = torch.empty(max(scratch_bytes, 16), dtype=torch.uint8, device=x.device)
         check(
             lib.fvc_conv_wgrad(

@@ -213,7 +213,7 @@ FVC_API int fvc_conv_forward(const void *x, const void *w_packed, const void *bi
  * fixed-order (deterministic) fp32/fp64 reduction.  offsets_host / offsets_dev: the same int64 [K^3+1]
  * CSR offsets on the host and on the device.  nbr/pitch: the output-stationary dense map of the same
  * rulebook (used by the tensor-core path; may be NULL, then the CSR path runs). */
-FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout,
+FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout,
                                     int64_t kernel_volume, int32_t dtype);
 FVC_API int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const int32_t *scatter,
                    const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,

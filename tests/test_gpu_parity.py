@@ -439,8 +439,8 @@ def test_fp32_tensor_core_split_matches_cuda_core_path(fvdb, positive):
             got[path] = (cpp.gs_conv(x, w, topo), *cpp.gs_conv_backward(dy, x, w, topo))
         finally:
             cpp.set_conv_path("auto")
-    for a, b in zip(got["simt"], got["auto"]):
-        assert _rel_err(b, a.cpu()) <= 5e-6
+    for a, b, tol in zip(got["simt"], got["auto"], (5e-6, 5e-6, 1e-5)):  # y, grad_features, grad_weights (longer reduction)
+        assert _rel_err(b, a.cpu()) <= tol
     want_y, want_gx, want_gw = _oracle_run(topo, x, w, dy)
     assert _rel_err(got["auto"][0], want_y) <= 1e-5 and _rel_err(got["auto"][1], want_gx) <= 1e-5
 
