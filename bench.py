@@ -437,13 +437,22 @@ def run_unet(args, cfg):
     up = [Plan.from_plan_transposed(p) for p in down]  # exact adjoint topology of the matching down-conv
 
     class Block(torch.nn.Module):
+        """conv -> BatchNorm -> ReLU.  Default: fvdb.nn.BatchNorm with the ReLU fused (csrc/norm.cu); --torch-bn runs the
+        reference's composition (torch.nn.BatchNorm1d over jdata, then a separate ReLU pass)."""
+
         def __init__(self, conv, channels):
             super().__init__()
-            self.conv, self.norm = conv, torch.nn.BatchNorm1d(channels)
+            self.conv = conv
+            if args.torch_bn:
+                self.norm = torch.nn.BatchNorm1d(channels)
+            else:
+                self.norm = (fvdb.nn.SyncBatchNorm if args.sync_bn else fvdb.nn.BatchNorm)(channels, activation="relu")
 
         def forward(self, x, plan):
             y = self.conv(x, plan)
-            return y.jagged_like(torch.relu(self.norm(y.jdata)))
+            if args.torch_bn:
+                return y.jagged_like(torch.relu(self.norm(y.jdata)))
+            return self.norm(y)
 
     class Stack(torch.nn.Module):
         def __init__(self):
@@ -508,6 +517,19 @@ def run_unet(args, cfg):
         barrier()
     launches = launch_count() - l0
     ms = a.elapsed_time(b) / args.steps
+    if args.profile and rank == 0:  # where does the step go?  (torch.profiler sees the ctypes-launched kernels through CUPTI)
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        from torch.autograd import DeviceType
+
+        events = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA and e.device_time_total > 0]
+        total = sum(e.device_time_total for e in events)
+        print(f"[profile] one step: GPU kernel time {total / 1e3:.2f} ms over {sum(e.count for e in events)} launches; wall {ms:.2f} ms", file=sys.stderr)
+        for e in sorted(events, key=lambda e: -e.device_time_total)[:25]:
+            print(f"[profile] {e.device_time_total / 1e3:9.3f} ms {e.count:5d}  {e.key[:110]}", file=sys.stderr)
     stats = torch.tensor([ms, float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         mx, sm = stats.clone(), stats.clone()
@@ -522,7 +544,8 @@ def run_unet(args, cfg):
             "metric": "sparse-conv voxels/sec fwd+bwd", "value": total_n / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
             "config": {"workload": cfg["desc"], "grids_per_gpu": grids_here, "voxels_per_gpu": n, "voxels_per_level": [g.total_voxels for g in grids],
-                       "pairs_3x3x3_per_level": pairs, "layers": "2x[3^3 c->c] per level, 2^3 s2 down 32-64-128-256, exact-transpose up, BN+ReLU in torch, SGD step",
+                       "pairs_3x3x3_per_level": pairs, "layers": "2x[3^3 c->c] per level, 2^3 s2 down 32-64-128-256, exact-transpose up, "
+                                 + ("BN+ReLU in torch" if args.torch_bn else ("fused SyncBatchNorm+ReLU" if args.sync_bn else "fused BatchNorm+ReLU") + " (csrc/norm.cu)") + ", SGD step",
                        "collective": f"{collectives} bucketed all_reduce(grad) calls per step" if world > 1 else "none"},
             "loss": float(loss), "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None, "e2e": None,
         }
@@ -539,6 +562,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="c3: print a torch.profiler kernel-time summary of one step to stderr")
+    ap.add_argument("--torch-bn", action="store_true", help="c3: torch BatchNorm1d + separate ReLU (the reference's composition) instead of the fused kernels")
+    ap.add_argument("--sync-bn", action="store_true", help="c3: batch statistics over all ranks (fvdb.nn.SyncBatchNorm)")
     ap.add_argument("--grids", type=int, default=0, help="override the number of grids per GPU (experiments)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])

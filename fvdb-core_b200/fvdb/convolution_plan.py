@@ -15,7 +15,7 @@ from typing import Any
 
 import torch
 
-from . import _fvdb_cpp
+from . import _fvdb_cpp, _norm
 from .enums import ConvolutionPhasePolicy, ConvolutionTopologyPolicy, ConvolutionTopologyProvenance
 from .grid_batch import GridBatch
 from .jagged_tensor import JaggedTensor
@@ -290,7 +290,8 @@ class _GatherScatterConvFn(torch.autograd.Function):
         fn = _fvdb_cpp.gs_conv_transpose_backward if ctx.transposed else _fvdb_cpp.gs_conv_backward
         grad_output = grad_output.contiguous()
         grad_features, grad_weights = fn(grad_output, features, weights, ctx.topo)
-        grad_bias = grad_output.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        # bias gradient: fp32 column sums in one streaming pass (csrc/norm.cu), rounded once
+        grad_bias = _norm.column_sums(grad_output).to(grad_output.dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return grad_features, grad_weights, grad_bias, None, None
 
 

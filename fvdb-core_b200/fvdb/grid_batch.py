@@ -36,6 +36,30 @@ class GridBatch:
         return cls(data)
 
     @classmethod
+    def from_points(cls, points: "JaggedTensor | torch.Tensor", voxel_sizes: NumericMaxRank2 = 1, origins: NumericMaxRank2 = 0) -> "GridBatch":
+        """Grid batch with one voxel per occupied point location (fvdb/grid_batch.py:389-409).
+
+        ``ijk = round(p / voxel_size - origin / voxel_size)`` in the points' own precision, exactly the primal
+        transform of src/fvdb/VoxelCoordTransform.h:300-310 applied by ops/BuildGridFromPoints.cu:89,119-124;
+        ``round`` is NanoVDB's ``Vec3::round`` = ``floor(x + 0.5)`` (recalled upstream convention: NanoVDB is not
+        vendored in the reference tree).  The coordinates then go through the same device builder as ``from_ijk``."""
+        if isinstance(points, torch.Tensor):
+            points = JaggedTensor(points)
+        if not points.jdata.is_floating_point():
+            raise TypeError("points must be a floating point JaggedTensor")
+        num_grids = points.num_tensors
+        sizes = to_Vec3fBatch(voxel_sizes, num_grids, "voxel_sizes", positive=True)
+        orig = to_Vec3fBatch(origins, num_grids, "origins")
+        pts = points.jdata.reshape(-1, 3)
+        math_dtype = torch.float64 if pts.dtype == torch.float64 else torch.float32
+        scale = (1.0 / sizes.double()).to(device=pts.device, dtype=math_dtype)
+        shift = (-orig.double() / sizes.double()).to(device=pts.device, dtype=math_dtype)
+        which = points.jidx.long() if num_grids > 1 else torch.zeros(pts.shape[0], dtype=torch.long, device=pts.device)
+        ijk = torch.floor(pts.to(math_dtype) * scale[which] + shift[which] + 0.5).to(torch.int32)
+        data = _fvdb_cpp.build_grid_from_ijk(ijk, points.jidx if num_grids > 1 else None, num_grids, sizes, orig)
+        return cls(data)
+
+    @classmethod
     def from_zero_voxels(cls, device="cuda", voxel_sizes: NumericMaxRank2 = 1, origins: NumericMaxRank2 = 0) -> "GridBatch":
         sizes = torch.as_tensor(voxel_sizes, dtype=torch.float64).reshape(-1, 3) if not isinstance(voxel_sizes, (int, float)) else None
         num_grids = 1 if sizes is None else int(sizes.shape[0])

@@ -1,3 +1,3 @@
-from .modules import SparseConv3d, SparseConvTranspose3d
+from .modules import BatchNorm, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm
 
-__all__ = ["SparseConv3d", "SparseConvTranspose3d"]
+__all__ = ["BatchNorm", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm"]

@@ -14,6 +14,7 @@ import torch
 from torch import nn
 from torch.profiler import record_function
 
+from .. import _norm
 from ..convolution_plan import ConvolutionPlan
 from ..jagged_tensor import JaggedTensor
 from ..types import NumericMaxRank1, ValueConstraint, to_Vec3i
@@ -73,3 +74,71 @@ class SparseConvTranspose3d(_SparseConv3dBase):
     """Sparse 3-D transposed convolution according to a transposed ConvolutionPlan."""
 
     _transposed = True
+
+
+class BatchNorm(nn.BatchNorm1d):
+    """Batch normalisation over the voxels of a JaggedTensor (mirror of reference fvdb/nn/modules.py:484-521: same
+    constructor, parameters / buffers and ``forward(data, grid)``), executed by the streaming kernels of csrc/norm.cu.
+
+    ``activation="relu"`` (extension, keyword only) fuses the ReLU that follows the norm in every block of the
+    reference's networks (fvdb/nn/simple_unet.py) into the same pass, forward and backward."""
+
+    _sync = False
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: "float | None" = 0.1, affine: bool = True,
+                 track_running_stats: bool = True, device=None, dtype=None, *, activation: "str | None" = None, process_group=None) -> None:
+        super().__init__(num_features, eps, momentum, affine, track_running_stats, device=device, dtype=dtype)
+        if activation not in (None, "relu"):
+            raise ValueError("activation must be None or 'relu'")
+        self.activation, self.process_group = activation, process_group
+
+    def _rows(self, x: torch.Tensor) -> torch.Tensor:
+        training = self.training or self.running_mean is None
+        momentum = 0.0 if self.momentum is None else self.momentum
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            if self.momentum is None:  # cumulative moving average
+                momentum = 1.0 / float(self.num_batches_tracked)
+        group = None
+        if self._sync and training:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+                group = self.process_group if self.process_group is not None else dist.group.WORLD
+        return _norm.batch_norm_rows(x, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
+                                     self.running_var if self.track_running_stats else None, training, momentum, self.eps,
+                                     relu=self.activation == "relu", group=group)
+
+    def forward(self, data: JaggedTensor, grid=None) -> JaggedTensor:  # type: ignore[override]
+        with record_function(repr(self)):
+            num_channels = data.jdata.size(1)
+            assert num_channels == self.num_features, "Input feature should have the same number of channels as BatchNorm"
+            out = self._rows(data.jdata)
+            return grid.jagged_like(out) if grid is not None else data.jagged_like(out)
+
+
+class SyncBatchNorm(BatchNorm):
+    """BatchNorm with statistics over every process of ``process_group`` (mirror of reference modules.py:524-580): the
+    per-rank (count, mean, M2) are all-gathered and merged, the two backward sums all-reduced (2*C floats each)."""
+
+    _sync = True
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: "float | None" = 0.1, affine: bool = True,
+                 track_running_stats: bool = True, process_group=None, device=None, dtype=None, *, activation: "str | None" = None) -> None:
+        super().__init__(num_features, eps, momentum, affine, track_running_stats, device=device, dtype=dtype, activation=activation,
+                         process_group=process_group)
+
+    @classmethod
+    def convert_sync_batchnorm(cls, module: nn.Module, process_group=None) -> nn.Module:
+        """Replace every fvdb.nn.BatchNorm in ``module`` by a SyncBatchNorm sharing its parameters and buffers."""
+        out = module
+        if isinstance(module, BatchNorm) and not isinstance(module, SyncBatchNorm):
+            out = cls(module.num_features, module.eps, module.momentum, module.affine, module.track_running_stats, process_group,
+                      activation=module.activation)
+            if module.affine:
+                out.weight, out.bias = module.weight, module.bias
+            out.running_mean, out.running_var, out.num_batches_tracked = module.running_mean, module.running_var, module.num_batches_tracked
+            out.training = module.training
+        for name, child in module.named_children():
+            out.add_module(name, cls.convert_sync_batchnorm(child, process_group))
+        return out

@@ -221,6 +221,31 @@ FVC_API int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather,
                    int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, void *grad_w,
                    void *scratch, size_t scratch_bytes, fvc_stream_t stream);
 
+/* -------- normalisation around the convolution (replaces torch.nn.BatchNorm1d over jdata
+ *          + the separate ReLU pass of fvdb/nn/modules.py:484-521,91-110 and the bias-gradient reduction) -------------
+ * Rows are [n][channels] row-major in `dtype` (f16 / bf16 / f32), channels a multiple of 16 bytes' worth of elements.
+ * Statistics, affine parameters and sums are fp32 [channels]; gamma / beta may be NULL (1 / 0).  `scratch` holds the
+ * per-CTA partials (fvc_bn_scratch_bytes).  All entry points are asynchronous on `stream` and deterministic. */
+FVC_API size_t fvc_bn_scratch_bytes(int32_t channels);
+/* mean / biased variance over the n rows; running_mean / running_var (may be NULL) are updated in place with `momentum`
+ * (running_var from the unbiased variance), as torch.nn.BatchNorm1d does in training mode. */
+FVC_API int fvc_bn_stats(const void *x, int64_t n, int32_t channels, int32_t dtype, float *mean, float *var, float *running_mean,
+                 float *running_var, float momentum, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
+/* y = act((x - mean) / sqrt(var + eps) * gamma + beta), act = ReLU when relu != 0 */
+FVC_API int fvc_bn_apply(const void *x, int64_t n, int32_t channels, int32_t dtype, const float *mean, const float *var, const float *gamma,
+                 const float *beta, float eps, int32_t relu, void *y, fvc_stream_t stream);
+/* sums[0][c] = sum dz (= grad beta), sums[1][c] = sum dz * xhat (= grad gamma); dz = dy masked by the fused ReLU */
+FVC_API int fvc_bn_backward_reduce(const void *dy, const void *x, int64_t n, int32_t channels, int32_t dtype, const float *mean, const float *var,
+                           const float *gamma, const float *beta, float eps, int32_t relu, float *sums, void *scratch, size_t scratch_bytes,
+                           fvc_stream_t stream);
+/* dx from dy, x and the (possibly all-reduced) sums over `count` rows; training == 0: statistics are constants */
+FVC_API int fvc_bn_backward_apply(const void *dy, const void *x, int64_t n, int32_t channels, int32_t dtype, const float *mean, const float *var,
+                          const float *gamma, const float *beta, float eps, int32_t relu, int32_t training, const float *sums, int64_t count,
+                          void *dx, fvc_stream_t stream);
+/* sums[c] = sum over rows of x[:, c] (bias gradient of SparseConv3d, fvdb/nn/modules.py:370-371) */
+FVC_API int fvc_column_sums(const void *x, int64_t n, int32_t channels, int32_t dtype, float *sums, void *scratch, size_t scratch_bytes,
+                    fvc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

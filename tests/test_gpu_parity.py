@@ -77,6 +77,26 @@ def test_grid_build_rows_order_and_lookup(fvdb):
     assert not bool(grid.coords_in_grid(miss).jdata.any())
 
 
+def test_from_points_voxelises_like_the_reference_transform(fvdb):
+    # ijk = round(p / voxel_size - origin / voxel_size), round = floor(x + 0.5)  (VoxelCoordTransform.h:300-310,
+    # BuildGridFromPoints.cu:89); per-grid voxel sizes and origins, negative coordinates, duplicate voxels merged.
+    gen = torch.Generator().manual_seed(17)
+    pts = [torch.randn((4000, 3), generator=gen) * 3.0, torch.rand((2500, 3), generator=gen) * 5.0 - 4.0]
+    sizes = torch.tensor([[0.25, 0.5, 0.125], [0.1, 0.1, 0.2]], dtype=torch.float64)
+    origins = torch.tensor([[0.05, -0.3, 0.0], [1.0, 2.0, -3.0]], dtype=torch.float64)
+    grid = fvdb.GridBatch.from_points(fvdb.JaggedTensor([p.to(DEV) for p in pts]), sizes, origins)
+    for b, p in enumerate(pts):
+        want = np.unique(np.floor(p.numpy().astype(np.float32) * (1.0 / sizes[b].numpy()).astype(np.float32)
+                                  + (-origins[b].numpy() / sizes[b].numpy()).astype(np.float32) + np.float32(0.5)).astype(np.int64), axis=0)
+        lo, hi = int(grid.joffsets[b]), int(grid.joffsets[b + 1])
+        got = grid.ijk.jdata[lo:hi].cpu().numpy().astype(np.int64)
+        assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+    torch.testing.assert_close(grid.voxel_sizes.cpu().double(), sizes)
+    torch.testing.assert_close(grid.origins.cpu().double(), origins)
+    with pytest.raises(TypeError):
+        fvdb.GridBatch.from_points(torch.zeros((4, 3), dtype=torch.int32, device=DEV))
+
+
 def test_neighbor_indexes_match_oracle(fvdb):
     grid = _grid(fvdb, _random_batch(2, n=2000, extent=12))
     ijk, b = _rows(grid)
@@ -494,3 +514,52 @@ def test_host_pipelined_conv_matches_plain_execution(fvdb):
     gx, gw = fvdb._fvdb_cpp.gs_conv_backward(dy_host.to(DEV), x_host.to(DEV), w, topo)
     assert torch.equal(y_host, y.cpu()) and torch.equal(gx_host, gx.cpu())  # same kernels on row sub-ranges: bit-identical
     assert _rel_err(gw_host, gw.float().cpu()) <= 1e-2  # chunk partials are summed in fp32, then rounded once
+
+
+@pytest.mark.parametrize("dtype,channels,relu,tol", [(torch.float32, 32, False, 2e-5), (torch.float32, 64, True, 2e-5), (torch.float32, 24, True, 2e-5),
+                                                     (torch.bfloat16, 64, True, 2e-2), (torch.bfloat16, 256, False, 2e-2), (torch.float16, 40, True, 5e-3)])
+def test_batch_norm_matches_torch_batch_norm1d(fvdb, dtype, channels, relu, tol):
+    # fvdb.nn.BatchNorm == torch.nn.BatchNorm1d over jdata (reference modules.py:484-521) [+ ReLU]: outputs, all three
+    # gradients and the running statistics, in training and in eval mode.
+    gen = torch.Generator().manual_seed(31)
+    coords = [_random_batch(40 + i, n=5000, extent=14, batches=1, dup=False)[0] for i in range(2)]
+    grid = _grid(fvdb, coords)
+    n = grid.total_voxels
+    x = (torch.randn((n, channels), generator=gen) * 1.7 + 0.6).to(dtype).to(DEV).requires_grad_()
+    dy = torch.randn((n, channels), generator=gen).to(dtype).to(DEV)
+    ours = fvdb.nn.BatchNorm(channels, activation="relu" if relu else None).to(DEV)
+    ref = torch.nn.BatchNorm1d(channels).to(DEV)
+    with torch.no_grad():
+        ours.weight.copy_(torch.rand(channels, generator=gen) + 0.5)
+        ours.bias.copy_(torch.randn(channels, generator=gen) * 0.3)
+        ref.weight.copy_(ours.weight)
+        ref.bias.copy_(ours.bias)
+    xr = x.detach().float().requires_grad_()
+    for step in range(2):  # two steps: running statistics accumulate
+        y = ours(grid.jagged_like(x), grid).jdata
+        yr = ref(xr)
+        yr = torch.relu(yr) if relu else yr
+    assert y.dtype == dtype and _rel_err(y.detach(), yr.detach().cpu()) <= tol
+    gx, gw, gb = torch.autograd.grad(y, (x, ours.weight, ours.bias), dy)
+    gxr, gwr, gbr = torch.autograd.grad(yr, (xr, ref.weight, ref.bias), dy.float())
+    assert _rel_err(gx, gxr.cpu()) <= tol and _rel_err(gw, gwr.cpu()) <= tol and _rel_err(gb, gbr.cpu()) <= tol
+    torch.testing.assert_close(ours.running_mean, ref.running_mean, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ours.running_var, ref.running_var, rtol=1e-4, atol=1e-4)
+    assert int(ours.num_batches_tracked) == 2 and set(ours.state_dict()) == set(ref.state_dict())
+    ours.eval(), ref.eval()
+    ye = ours(grid.jagged_like(x), grid).jdata
+    yer = torch.relu(ref(xr)) if relu else ref(xr)
+    assert _rel_err(ye.detach(), yer.detach().cpu()) <= tol
+    (gxe,) = torch.autograd.grad(ye, x, dy)
+    (gxer,) = torch.autograd.grad(yer, xr, dy.float())
+    assert _rel_err(gxe, gxer.cpu()) <= tol
+
+
+def test_bias_gradient_column_sums(fvdb):
+    from fvdb import _norm
+
+    gen = torch.Generator().manual_seed(2)
+    for dtype, c in ((torch.float32, 32), (torch.bfloat16, 64), (torch.float16, 16), (torch.float32, 5)):
+        x = torch.randn((70001, c), generator=gen).to(dtype).to(DEV)
+        got = _norm.column_sums(x)
+        assert got.dtype == torch.float32 and _rel_err(got, x.double().sum(0).float().cpu()) <= 1e-6
