@@ -41,15 +41,16 @@ CONFIGS = {
     "c3": dict(gen="indoor_room", grids=16, voxels=150_000, kernel=3, cin=32, cout=32, dtype="bf16", desc="C3 sparse UNet block stack (3^3 convs, 2^3 s2 down, transposed up, 32..256 ch) on 16 indoor grids, training step"),
     "c2f32": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=64, cout=64, dtype="f32", desc="C2-shaped 8 grids x ~200k voxels, 3^3 64->64 fp32 fwd+bwd (three-way bf16 split on the tensor pipe)"),
     "c2x128": dict(gen="indoor_room", grids=8, voxels=200_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C2-shaped 8 grids x ~200k voxels, 3^3 128->128 bf16 fwd+bwd"),
-    "c4": dict(gen="lidar_sweep", grids=32, voxels=1_000_000, kernel=3, cin=128, cout=128, dtype="bf16", desc="C4 KITTI-shaped 32 grids x ~1M voxels, 3^3 128->128 bf16"),
+    "c4": dict(gen="lidar_sweep", grids=32, voxels=1_000_000, kernel=3, cin=128, cout=128, dtype="bf16", partition="by_grid",
+               desc="C4 KITTI-shaped 32 grids x ~1M voxels, 3^3 128->128 bf16, GridBatch partitioned by grid"),
     "c5": dict(gen="random_occupancy", grids=8, voxels=4_979_000, kernel=5, cin=16, cout=16, dtype="bf16", desc="C5 8 grids x ~5M voxels, 5^3 16->16"),
 }
 DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16, "f64": torch.float64}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same command
-# (profiles/r01_ncu_full_v5_summary.txt); only known for the default workload.
-NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 171.2e6, "dgrad": 297.7e6 + 171.2e6, "wgrad": 565.9e6 + 7.5e6}}
+# (profiles/r01_ncu_full_v6_summary.txt); only known for the default workload.
+NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 168.6e6, "dgrad": 297.7e6 + 168.6e6, "wgrad": 595.2e6 + 10.1e6}}
 
 
 def load_peaks() -> dict:
@@ -60,10 +61,19 @@ def load_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def make_coords(cfg: dict, rank: int, device) -> list[torch.Tensor]:
+def make_coords(cfg: dict, rank: int, device, world: int = 1) -> list[torch.Tensor]:
+    """This rank's grids.  Weak scaling (default): every rank builds its own cfg["grids"] grids.  cfg["partition"] ==
+    "by_grid" (C4): the batch of cfg["grids"] grids is ONE job partitioned by grid -- every rank generates the whole
+    batch (same seeds), bin-packs it by voxel count (LPT) and keeps its share, so no data crosses ranks."""
     from fvdb.utils import synthetic
 
     gen = getattr(synthetic, cfg["gen"])
+    if cfg.get("partition") == "by_grid" and world > 1:
+        from fvdb.distributed import partition_grids_lpt
+
+        every = make_coords({**cfg, "partition": None}, 0, device, 1)
+        mine = partition_grids_lpt([int(c.shape[0]) for c in every], world)[rank]
+        return [every[g] for g in mine]
     out = []
     for g in range(cfg["grids"]):
         seed = rank * 1000 + g
@@ -207,7 +217,8 @@ def run_ours(args, cfg):
 
     dtype = DTYPES[cfg["dtype"]]
     k, cin, cout = cfg["kernel"], cfg["cin"], cfg["cout"]
-    coords = make_coords(cfg, rank, dev)
+    coords = make_coords(cfg, rank, dev, world)
+    strong = cfg.get("partition") == "by_grid"
     grid = fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(coords))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -380,13 +391,13 @@ def run_ours(args, cfg):
                    "sample": f"1 of {cfg['grids']} grids ({vox} voxels, {pairs} pairs) fwd+bwd fp32, median of 2 after 1 warm-up; oracle port of the GatherScatterDefault CPU path"}
         roof = dict(per_kernel[dominant])
         traffic = NCU_TRAFFIC_BYTES.get(args.config, {}).get(dominant) if cfg["grids"] == CONFIGS[args.config]["grids"] else None
-        roof.update({"kernel": dominant, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_ncu_full_v5_summary.txt" if traffic else None,
+        roof.update({"kernel": dominant, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_ncu_full_v6_summary.txt" if traffic else None,
                      "peak_source": peaks["source"]})
         line = {
             "metric": "sparse-conv voxels/sec fwd+bwd", "value": total_n / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": cfg["dtype"],
             "data": "synthetic",
-            "config": {"workload": cfg["desc"], "grids_per_gpu": cfg["grids"], "voxels_per_gpu": n, "pairs_per_gpu": P, "pairs_per_voxel": P / max(n, 1),
+            "config": {"workload": cfg["desc"], "grids_per_gpu": len(coords), "voxels_per_gpu": n, "pairs_per_gpu": P, "pairs_per_voxel": P / max(n, 1),
                        "kernel": f"{k}^3 stride 1 same-topology", "channels": f"{cin}->{cout}", "l2_policy": "inputs larger than L2 (features+grads+maps > 126 MB)",
                        "collective": "all_reduce(grad_weights)" if world > 1 else "none", "plan_build_ms": plan_ms},
             "voxel_features_per_s": total_n * (cin + cout) / 2 / (ms * 1e-3),
@@ -507,15 +518,46 @@ def run_unet(args, cfg):
     for _ in range(args.warmup):
         step()
     barrier()
+    run_step, graph_note = step, "eager launches"
+    if args.graph and world == 1:
+        # the whole training step (forward, backward, SGD update) as ONE CUDA graph: every kernel of the step -- ours through
+        # the C ABI and torch's elementwise ones -- is captured on a side stream once and replayed per step
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l_cap = launch_count()
+            with torch.cuda.graph(graph, stream=side):
+                static_loss = step()
+            launches_per_replay = launch_count() - l_cap
+
+            def run_step():
+                graph.replay()
+                return static_loss
+
+            graph_note = f"CUDA graph replay ({launches_per_replay} of our kernels + torch's per step in one graph launch)"
+            for _ in range(2):
+                run_step()
+            torch.cuda.synchronize()
+        except Exception as exc:  # capture is an optimisation; say so rather than hide it
+            torch.cuda.synchronize()
+            run_step, graph_note = step, f"eager launches (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
     l0 = launch_count()
     with ClockSampler(local_rank) as clocks:
         a, b = ev(), ev()
         a.record()
         for _ in range(args.steps):
-            loss = step()
+            loss = run_step()
         b.record()
         barrier()
     launches = launch_count() - l0
+    if graph_note.startswith("CUDA graph"):
+        launches = launches_per_replay * args.steps
     ms = a.elapsed_time(b) / args.steps
     if args.profile and rank == 0:  # where does the step go?  (torch.profiler sees the ctypes-launched kernels through CUPTI)
         from torch.profiler import ProfilerActivity, profile
@@ -546,7 +588,7 @@ def run_unet(args, cfg):
             "config": {"workload": cfg["desc"], "grids_per_gpu": grids_here, "voxels_per_gpu": n, "voxels_per_level": [g.total_voxels for g in grids],
                        "pairs_3x3x3_per_level": pairs, "layers": "2x[3^3 c->c] per level, 2^3 s2 down 32-64-128-256, exact-transpose up, "
                                  + ("BN+ReLU in torch" if args.torch_bn else ("fused SyncBatchNorm+ReLU" if args.sync_bn else "fused BatchNorm+ReLU") + " (csrc/norm.cu)") + ", SGD step",
-                       "collective": f"{collectives} bucketed all_reduce(grad) calls per step" if world > 1 else "none"},
+                       "collective": f"{collectives} bucketed all_reduce(grad) calls per step" if world > 1 else "none", "launch_mode": graph_note},
             "loss": float(loss), "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None, "e2e": None,
         }
         print(json.dumps(line), flush=True)
@@ -562,6 +604,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="c3 (1 GPU): capture the training step in one CUDA graph and replay it")
     ap.add_argument("--profile", action="store_true", help="c3: print a torch.profiler kernel-time summary of one step to stderr")
     ap.add_argument("--torch-bn", action="store_true", help="c3: torch BatchNorm1d + separate ReLU (the reference's composition) instead of the fused kernels")
     ap.add_argument("--sync-bn", action="store_true", help="c3: batch statistics over all ranks (fvdb.nn.SyncBatchNorm)")

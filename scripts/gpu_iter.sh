@@ -1,5 +1,6 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "batch_norm or column_sums or from_points" 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --config c3 --steps 5 --warmup 3 --profile 2>&1 | tail -30 | cut -c1-200 | tee gpurun_out/bench_c3_profile.txt
+timeout 600 python bench.py --config c3 --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_c3.json | cut -c1-1300
+timeout 600 python bench.py --config c3 --steps 10 --warmup 3 --graph 2>&1 | tail -3 | tee gpurun_out/bench_c3_graph.json | cut -c1-1300
+timeout 600 python bench.py --config c3 --steps 10 --warmup 3 --torch-bn 2>&1 | tail -1 | tee gpurun_out/bench_c3_torchbn.json | cut -c1-300
