@@ -464,7 +464,7 @@ def _forward(features, weights, topo, name, want_transposed, bias=None):
         return _run_conv(features, w, topo._out_map(), topo.feature_total_voxels, topo.output_total_voxels, cin, cout, topo.kernel_volume, bias, topo._out_mask())
 
 
-def _backward(grad_output, features, weights, topo, name, want_transposed):
+def _backward(grad_output, features, weights, topo, name, want_transposed, on_grad_weights=None):
     _check_conv(features, weights, topo, name)
     if topo.is_transposed != want_transposed:
         raise RuntimeError(f"{name} requires {'direction=Transposed' if want_transposed else 'topology with direction=Forward'}")
@@ -484,13 +484,8 @@ def _backward(grad_output, features, weights, topo, name, want_transposed):
     device = features.device
     code = _DTYPE_CODE[working]
     with torch.cuda.device(device):
-        # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (GatherScatterDefault.cu:803-804), output-stationary over features
-        wt = _pack_weights(weights, working, layout=1)
-        if n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
-            grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
-        else:
-            grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3, None, topo._in_mask())
-        # wgrad: dW[k] = X[g]^T . dY[s]  (:806-813)
+        # wgrad first: dW[k] = X[g]^T . dY[s]  (GatherScatterDefault.cu:806-813).  Its result is the only thing a data-parallel
+        # job exchanges, so `on_grad_weights` (e.g. an asynchronous NCCL all-reduce) can overlap the dgrad kernel below.
         grad_weights = torch.empty(tuple(weights.shape), dtype=working, device=device)
         scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, topo.total_pairs, cin, cout, k3, code))
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
@@ -503,6 +498,14 @@ def _backward(grad_output, features, weights, topo, name, want_transposed):
                 _ptr(topo._out_mask()), n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
             )
         )
+        if on_grad_weights is not None:
+            on_grad_weights(grad_weights)
+        # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (:803-804), output-stationary over features
+        wt = _pack_weights(weights, working, layout=1)
+        if n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
+            grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
+        else:
+            grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3, None, topo._in_mask())
     return grad_features, grad_weights
 
 
@@ -511,9 +514,10 @@ def gs_conv(features, weights, topology, bias=None):
     return _forward(features, weights, topology, "gatherScatterDefaultSparseConv", False, bias)
 
 
-def gs_conv_backward(grad_output, features, weights, topology):
-    """(grad_features, grad_weights) of the forward convolution (Bindings.cpp:595-609)."""
-    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvBackward", False)
+def gs_conv_backward(grad_output, features, weights, topology, on_grad_weights=None):
+    """(grad_features, grad_weights) of the forward convolution (Bindings.cpp:595-609).  ``on_grad_weights(grad_weights)``
+    (extension) is called as soon as the weight gradient is enqueued, before the dgrad kernel."""
+    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvBackward", False, on_grad_weights)
 
 
 def gs_conv_transpose(features, weights, topology, bias=None):
@@ -521,9 +525,9 @@ def gs_conv_transpose(features, weights, topology, bias=None):
     return _forward(features, weights, topology, "gatherScatterDefaultSparseConvTranspose", True, bias)
 
 
-def gs_conv_transpose_backward(grad_output, features, weights, topology):
+def gs_conv_transpose_backward(grad_output, features, weights, topology, on_grad_weights=None):
     """(grad_features, grad_weights) of the transposed convolution (Bindings.cpp:638-653)."""
-    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvTransposeBackward", True)
+    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvTransposeBackward", True, on_grad_weights)
 
 
 def pred_gather_igemm_conv(features, weights, feature_grid, output_grid, kernel_size: int, stride: int):
