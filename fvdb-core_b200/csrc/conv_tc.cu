@@ -31,7 +31,10 @@
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
 
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
 #include <cstdlib>
+#include <cstring>
 
 namespace fvc {
 
@@ -48,7 +51,7 @@ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 1
 
 // Small channel counts are packed: a 64-wide reduction block holds G = 64 / CIN consecutive taps x CIN channels
 // ("tap group"), so Cin = 16 / 32 feed the same K = 64 pipeline (the bandwidth-bound small-channel path).
-template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT = false> struct TcFwdCfg {
+template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT = false, bool TMA = false> struct TcFwdCfg {
     static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per reduction block
     static constexpr int KB = CIN >= 64 ? CIN / 64 : 1;     // 64-wide reduction blocks per tap group
     static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a 128-byte row
@@ -58,15 +61,17 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static constexpr int B_BYTES = NS * CHUNK_BYTES;         // one weight stage: the chunk(s) of one (tap group, channel block)
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * COUT;  // TMEM columns per tile (SPLIT: main | small-term accumulator)
     static constexpr int TMEM_COLS = tmem_cols_for(TILES * ACC_COLS);
-    static constexpr int MAX_UNITS = SPLIT ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS;
+    static constexpr int MAX_UNITS = (SPLIT || TMA) ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS;
     static constexpr int THREADS = (PW + 3) * 32;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * BST + 1 + 2 * TC_IDX_RING;
     // one ring entry: 128 map entries per tap of the group; with several taps per entry each tap's 512 bytes are followed
     // by a 16-byte pad, so the four taps a quarter-warp reads together sit on different banks
     static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;
     static constexpr int RING_BYTES = G * SUB_STRIDE;
-    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TC_IDX_RING) * RING_BYTES +
+    // TMA gather: the producer lanes read their four map entries straight from global memory, no ring
+    static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TMA ? 0 : TC_IDX_RING) * RING_BYTES +
                                    size_t(MAX_UNITS) * 2 + 8 * NUM_BARS + 16;
+    static_assert(!TMA || CIN >= 64, "the TMA gather path needs one tap per 128-byte row");
     // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (228 KB per SM, 1 KB reserved per CTA)
     static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = int(233472 / (SMEM + 1024 + 768));
     static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > 2 ? 2 : BY_TMEM) : (BY_SMEM > 2 ? 2 : BY_SMEM);
@@ -184,12 +189,13 @@ __device__ __forceinline__ float half_to_float(uint16_t v, bool bf16) {
 }
 
 // x: feature rows (SPLIT: the bf16 split rows [N][3][CIN]); bias / y: in the output dtype (SPLIT: fp32)
-template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT>
-__global__ void __launch_bounds__((PW + 3) * 32, (TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>::CTAS_PER_SM))
+template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT, bool TMA>
+__global__ void __launch_bounds__((PW + 3) * 32, (TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT, TMA>::CTAS_PER_SM))
 conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_img, const void *__restrict__ bias_,
                    void *__restrict__ y_, const int32_t *__restrict__ nbr, int64_t pitch,
-                   const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, uint32_t idesc, int is_bf16) {
-    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>;
+                   const unsigned long long *__restrict__ tile_mask, int64_t n_in, int64_t n_out, int k3, uint32_t idesc, int is_bf16,
+                   const __grid_constant__ CUtensorMap tmap) {
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT, TMA>;
     constexpr int KB = Cfg::KB, G = Cfg::G, CPT = Cfg::CPT, THREADS = Cfg::THREADS, NS = Cfg::NS, XS = Cfg::XS, ACC = Cfg::ACC_COLS;
     constexpr int WARP_MMA = PW, WARP_B = PW + 1;
     extern __shared__ uint8_t smem_raw[];
@@ -197,7 +203,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
     const uint32_t smem_idx = smem_b + BST * Cfg::B_BYTES;
-    const uint32_t smem_units = smem_idx + TC_IDX_RING * Cfg::RING_BYTES;
+    const uint32_t smem_units = smem_idx + (TMA ? 0 : TC_IDX_RING) * Cfg::RING_BYTES;
     const uint32_t bars = smem_units + Cfg::MAX_UNITS * 2;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 8 * BST;
@@ -235,7 +241,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, PW * 32); // one completion-triggered arrival per producer thread
+            mbar_init(bar_full + 8 * s, TMA ? 1 : PW * 32); // one completion-triggered arrival per producer thread (TMA: expect_tx)
             mbar_init(bar_empty + 8 * s, 1);      // tcgen05.commit
         }
         for (int b = 0; b < BST; ++b) {
@@ -289,6 +295,46 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     const int nunits = s_nunits;
 
     if (warp < PW) {
+        if constexpr (TMA) {
+            // ================= TMA gather producer (warp 0): one cp.async.bulk.tensor ... tile::gather4 per lane =================
+            // Lane l owns rows 4l .. 4l+3 of the tile: it reads their four map entries with one 128-bit load (the warp reads
+            // the unit's 512 bytes of map coalesced, one unit ahead) and issues ONE gather4 that lands the four 128-byte
+            // feature rows in the stage with the SWIZZLE_128B pattern the MMA descriptors expect; a missing neighbour is an
+            // out-of-range row coordinate, which the TMA unit zero-fills.  Completion is counted in bytes on the stage barrier.
+            if (warp == 0) {
+                const int32_t *lane_nbr = nbr + tile0 * TC_TILE_M + lane * 4;
+                const int miss = int(n_in < 0x7fffffff ? n_in : 0x7fffffff); // first out-of-range row
+                auto load_idx = [&](uint32_t unit) {
+                    const int g = int(unit >> 7), t = unit & 7;
+                    return __ldg(reinterpret_cast<const int4 *>(lane_nbr + int64_t(g) * pitch + t * TC_TILE_M));
+                };
+                int4 idx_next = nunits > 0 ? load_idx(units[0]) : make_int4(-1, -1, -1, -1);
+                int s = 0;
+                uint32_t ph = 0;
+                for (int u = 0; u < nunits; ++u) {
+                    const uint32_t unit = units[u];
+                    const int j = (unit >> 5) & 3, t = unit & 7;
+                    int4 idx = idx_next;
+                    if (u + 1 < nunits)
+                        idx_next = load_idx(units[u + 1]);
+                    const int64_t rows_left = n_out - (tile0 + t) * TC_TILE_M - lane * 4;
+                    idx.x = (idx.x >= 0 && 0 < rows_left) ? idx.x : miss;
+                    idx.y = (idx.y >= 0 && 1 < rows_left) ? idx.y : miss;
+                    idx.z = (idx.z >= 0 && 2 < rows_left) ? idx.z : miss;
+                    idx.w = (idx.w >= 0 && 3 < rows_left) ? idx.w : miss;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    if (lane == 0)
+                        mbar_expect_tx(bar_full + 8 * s, TC_A_BYTES);
+                    __syncwarp();
+                    const int col = j * 64 + (SPLIT ? int((unit >> 3) & 3u) * CIN : 0);
+                    tma_gather4(smem_a + s * TC_A_BYTES + lane * 512, &tmap, col, idx.x, idx.y, idx.z, idx.w, bar_full + 8 * s);
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        } else {
         // ================= gather producers: warp w copies rows [RPW*w, RPW*(w+1)) =================
         // lane = (lg, q): 8 lanes q cover one 128-byte row (one full line).  With one tap per row (Cin >= 64) lane group
         // lg takes rows lg, lg + 4, ... (an instruction copies 4 consecutive output rows, whose neighbours tend to be
@@ -351,6 +397,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             }
         }
         cp_async_wait_all();
+        }
 
         // ================= epilogue: warp w drains TMEM lanes 32*(w&3).. of tiles w>>2, w>>2 + PW/4, ... =================
         mbar_wait(bar_accum, 0);
@@ -498,7 +545,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     } else {
         // ================= kernel-map streamer (whole warp): 128 map entries = 32 lanes x 16 B per unit =================
         const int32_t *lane_nbr = nbr + tile0 * TC_TILE_M + lane * 4;
-        for (int u = 0; u < nunits; ++u) {
+        for (int u = 0; !TMA && u < nunits; ++u) {
             const uint32_t unit = units[u];
             const int g = int(unit >> 7), t = unit & 7;
             const int e = u & (TC_IDX_RING - 1);
@@ -524,10 +571,40 @@ static inline size_t tc_image_bytes(int32_t cin, int32_t cout, int64_t k3, int s
     return align_up(size_t(tc_groups(k3, cin)) * size_t(kb) * size_t(splits) * size_t(cout) * 128, 256);
 }
 
-template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT = false>
+// 2-D tensor map over feature rows [n_rows][row_elems] (2-byte elements) for tile::gather4: box = {64 elements, 1 row},
+// SWIZZLE_128B, zero fill out of range.  The encoder comes from the driver through the runtime (no libcuda link).
+static int make_row_gather_map(const void *rows, int64_t n_rows, int64_t row_elems, CUtensorMap *map) {
+    using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        FVC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status));
+        FVC_REQUIRE(fn && status == cudaDriverEntryPointSuccess, FVC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {cuuint64_t(row_elems), cuuint64_t(n_rows > 0 ? n_rows : 1)};
+    const cuuint64_t strides[1] = {cuuint64_t(row_elems) * 2};
+    const cuuint32_t box[2] = {64, 1}, elem_strides[2] = {1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(rows), dims, strides, box, elem_strides,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FVC_REQUIRE(rc == CUDA_SUCCESS, FVC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", int(rc));
+    return FVC_OK;
+}
+
+template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT = false, bool TMA = false>
 static int launch_tc_fwd(const ConvArgs &a, const void *x, const uint8_t *w_img) {
-    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>;
-    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES, BST, PW, SPLIT>;
+    using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT, TMA>;
+    auto kernel = conv_tc_fwd_kernel<CIN, COUT, TILES, STAGES, BST, PW, SPLIT, TMA>;
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (TMA) {
+        const int rc = make_row_gather_map(x, a.n_in, Cfg::XS, &tmap);
+        if (rc)
+            return rc;
+    }
     static bool configured = false; // per instantiation
     if (!configured) {
         FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
@@ -540,8 +617,8 @@ static int launch_tc_fwd(const ConvArgs &a, const void *x, const uint8_t *w_img)
     const bool bf16 = SPLIT || a.dtype == FVC_BF16;
     const uint32_t idesc = make_idesc_f16(TC_TILE_M, COUT, bf16, false, false);
     kernel<<<grid, Cfg::THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(x), w_img, a.bias, a.y, a.nbr, a.pitch,
-                                                        reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out, a.k3, idesc,
-                                                        bf16 ? 1 : 0);
+                                                        reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_in, a.n_out, a.k3,
+                                                        idesc, bf16 ? 1 : 0, tmap);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }
@@ -628,6 +705,9 @@ int tc_forward(const ConvArgs &a) {
         case 2: return launch_tc_fwd<64, 64, 8, 8, 4, 4>(a, a.x, img);
         case 3: return launch_tc_fwd<64, 64, 4, 3, 3, 4>(a, a.x, img);
         case 4: return launch_tc_fwd<64, 64, 2, 4, 3, 4>(a, a.x, img);
+        case 10: return launch_tc_fwd<64, 64, 4, 4, 3, 4, false, true>(a, a.x, img); // TMA gather4 producer
+        case 11: return launch_tc_fwd<64, 64, 4, 5, 3, 4, false, true>(a, a.x, img);
+        case 12: return launch_tc_fwd<64, 64, 4, 3, 3, 4, false, true>(a, a.x, img);
         default: break;
         }
     }
