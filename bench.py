@@ -521,7 +521,7 @@ def run_unet(args, cfg):
         step()
     barrier()
     run_step, graph_note = step, "eager launches"
-    if args.graph and world == 1:
+    if args.graph and world == 1:  # (capturing the NCCL all-reduce with the step hung at N = 2 on this stack: eager there)
         # the whole training step (forward, backward, SGD update) as ONE CUDA graph: every kernel of the step -- ours through
         # the C ABI and torch's elementwise ones -- is captured on a side stream once and replayed per step
         try:

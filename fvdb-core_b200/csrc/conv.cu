@@ -56,7 +56,8 @@ int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const i
                    const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                    int32_t path, void *grad_w, void *scratch, size_t scratch_bytes, fvc_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    int rc = check_common(x, dy, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_wgrad");
+    // (dy stands in for the weights argument of the shared check; it may be NULL only when there are no output rows)
+    int rc = check_common(x, n_out == 0 ? reinterpret_cast<const void *>(1) : dy, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_wgrad");
     if (rc)
         return rc;
     FVC_REQUIRE(path >= 0 && path <= 2, FVC_ERR_VALUE, "path must be 0 (auto), 1 (CUDA-core) or 2 (tensor-core)");

@@ -287,7 +287,8 @@ template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_backward_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, int64_t n, int c, const float *__restrict__ mean,
                          const float *__restrict__ var, const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int relu,
-                         int training, const float *__restrict__ sums /*[2][C]*/, float inv_count, T *__restrict__ dx) {
+                         int training, const float *__restrict__ sums /*[2][C]*/, float inv_count, const float *__restrict__ count_dev,
+                         T *__restrict__ dx) {
     constexpr int V = RowVec<T>::V;
     const Split sp = make_split<T>(c);
     const int tid = threadIdx.x;
@@ -295,6 +296,8 @@ bn_backward_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, int6
         return;
     const int col = tid % sp.cv;
     float mu[V], inv[V], g[V], b[V], m_dz[V], m_dzx[V];
+    if (count_dev) // total row count of a distributed batch, kept on the device (no host round trip)
+        inv_count = 1.f / fmaxf(__ldg(count_dev), 1.f);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
         const int ch = col * V + i;
@@ -433,7 +436,7 @@ int fvc_bn_backward_reduce(const void *dy, const void *x, int64_t n, int32_t c, 
 
 int fvc_bn_backward_apply(const void *dy, const void *x, int64_t n, int32_t c, int32_t dtype, const float *mean, const float *var,
                           const float *gamma, const float *beta, float eps, int32_t relu, int32_t training, const float *sums, int64_t count,
-                          void *dx, fvc_stream_t stream_) {
+                          const float *count_dev, void *dx, fvc_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_rows("fvc_bn_backward_apply", n, c, dtype);
     if (rc)
@@ -446,7 +449,7 @@ int fvc_bn_backward_apply(const void *dy, const void *x, int64_t n, int32_t c, i
         const Split sp = make_split<T>(c);
         bn_backward_apply_kernel<T><<<bn_grid(n, sp.rpb), BN_THREADS, 0, stream>>>(reinterpret_cast<const T *>(dy), reinterpret_cast<const T *>(x), n, c,
                                                                                   mean, var, gamma, beta, eps, relu, training, sums, inv_count,
-                                                                                  reinterpret_cast<T *>(dx));
+                                                                                  count_dev, reinterpret_cast<T *>(dx));
     });
     FVC_LAUNCH_CHECK();
     return FVC_OK;

@@ -61,7 +61,7 @@ class BatchNormFn(torch.autograd.Function):
         code = _CODES[x.dtype]
         gamma, beta = _f32(weight), _f32(bias)
         scratch = _scratch(x)
-        count = n
+        count, count_dev = n, None
         with torch.cuda.device(x.device):
             stream = _stream(x)
             if training:
@@ -81,23 +81,24 @@ class BatchNormFn(torch.autograd.Function):
                     total = counts.sum()
                     mean64 = (g[:, :c] * counts).sum(0) / total
                     m2 = g[:, c:2 * c].sum(0) + (counts * (g[:, :c] - mean64) ** 2).sum(0)
-                    mean, var, count = mean64.float(), (m2 / total).float(), int(total.item())
+                    mean, var, count_dev = mean64.float(), (m2 / total).float(), total.float().reshape(1)  # the count stays on the device
                 if running_mean is not None and not in_place:
-                    unbiased = var * (count / max(count - 1, 1))
+                    unbiased = var * (count_dev / (count_dev - 1).clamp_min(1)) if count_dev is not None else var * (count / max(count - 1, 1))
                     running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
                     running_var.mul_(1 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
             else:
                 mean, var = _f32(running_mean), _f32(running_var)
             y = torch.empty_like(x)
             check(lib.fvc_bn_apply(x.data_ptr(), n, c, code, mean.data_ptr(), var.data_ptr(), _p(gamma), _p(beta), float(eps), int(relu), y.data_ptr(), stream))
-        ctx.save_for_backward(x, mean, var, gamma if gamma is not None else x.new_empty(0), beta if beta is not None else x.new_empty(0))
+        ctx.save_for_backward(x, mean, var, gamma if gamma is not None else x.new_empty(0), beta if beta is not None else x.new_empty(0),
+                              count_dev if count_dev is not None else x.new_empty(0))
         ctx.cfg = (bool(training), float(eps), bool(relu), group, count, weight is not None, bias is not None,
                    None if weight is None else weight.dtype, None if bias is None else bias.dtype)
         return y
 
     @staticmethod
     def backward(ctx, grad_output):  # type: ignore[override]
-        x, mean, var, gamma, beta = ctx.saved_tensors
+        x, mean, var, gamma, beta, count_dev = ctx.saved_tensors
         training, eps, relu, group, count, has_w, has_b, w_dtype, b_dtype = ctx.cfg
         gamma = gamma if has_w else None
         beta = beta if has_b else None
@@ -119,7 +120,7 @@ class BatchNormFn(torch.autograd.Function):
                 dist.all_reduce(sums, group=group)
             if dx is not None:
                 check(lib.fvc_bn_backward_apply(dy.data_ptr(), x.data_ptr(), n, c, code, mean.data_ptr(), var.data_ptr(), _p(gamma), _p(beta), eps, int(relu),
-                                                int(training), sums.data_ptr(), count, dx.data_ptr(), stream))
+                                                int(training), sums.data_ptr(), count, count_dev.data_ptr() if count_dev.numel() else 0, dx.data_ptr(), stream))
         grad_w = local[1].to(w_dtype) if has_w and ctx.needs_input_grad[1] else None
         grad_b = local[0].to(b_dtype) if has_b and ctx.needs_input_grad[2] else None
         return dx, grad_w, grad_b, None, None, None, None, None, None, None

@@ -238,10 +238,11 @@ FVC_API int fvc_bn_apply(const void *x, int64_t n, int32_t channels, int32_t dty
 FVC_API int fvc_bn_backward_reduce(const void *dy, const void *x, int64_t n, int32_t channels, int32_t dtype, const float *mean, const float *var,
                            const float *gamma, const float *beta, float eps, int32_t relu, float *sums, void *scratch, size_t scratch_bytes,
                            fvc_stream_t stream);
-/* dx from dy, x and the (possibly all-reduced) sums over `count` rows; training == 0: statistics are constants */
+/* dx from dy, x and the (possibly all-reduced) sums over `count` rows (count_dev, if not NULL, is a device float holding
+ * the row count of a distributed batch and overrides `count`); training == 0: statistics are constants */
 FVC_API int fvc_bn_backward_apply(const void *dy, const void *x, int64_t n, int32_t channels, int32_t dtype, const float *mean, const float *var,
                           const float *gamma, const float *beta, float eps, int32_t relu, int32_t training, const float *sums, int64_t count,
-                          void *dx, fvc_stream_t stream);
+                          const float *count_dev, void *dx, fvc_stream_t stream);
 /* sums[c] = sum over rows of x[:, c] (bias gradient of SparseConv3d, fvdb/nn/modules.py:370-371) */
 FVC_API int fvc_column_sums(const void *x, int64_t n, int32_t channels, int32_t dtype, float *sums, void *scratch, size_t scratch_bytes,
                     fvc_stream_t stream);

@@ -563,3 +563,94 @@ def test_bias_gradient_column_sums(fvdb):
         x = torch.randn((70001, c), generator=gen).to(dtype).to(DEV)
         got = _norm.column_sums(x)
         assert got.dtype == torch.float32 and _rel_err(got, x.double().sum(0).float().cpu()) <= 1e-6
+
+
+# ------------------------------------------------------------------ edge cases and full-size properties
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_empty_and_degenerate_batches(fvdb, dtype):
+    # GatherScatterDefault.cu:698-699,771-777: O == 0 / P == 0 -> zeros of the right shape; empty batch items are preserved
+    # (BuildGridForConv.cu:372-389); a single voxel; a target grid disjoint from the source (no pairs at all).
+    cpp = fvdb._fvdb_cpp
+    w = (torch.ones((32, 32, 3, 3, 3)) / 8).to(dtype).to(DEV).requires_grad_()
+    # (a) batch with an empty item in the middle
+    coords = [_random_batch(1, n=900, extent=8, batches=1)[0], np.zeros((0, 3), dtype=np.int64), _random_batch(2, n=700, extent=8, batches=1)[0]]
+    grid = _grid(fvdb, coords)
+    assert grid.grid_count == 3 and grid.num_voxels_at(1) == 0
+    plan = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid, grid)
+    x = torch.randn((grid.total_voxels, 32)).to(dtype).to(DEV).requires_grad_()
+    y = plan.execute(grid.jagged_like(x), w)
+    want = _oracle_run(plan._backend.topology, x.detach(), w.detach(), torch.ones_like(y.jdata))[0]
+    assert _rel_err(y.jdata.detach(), want) <= (1e-5 if dtype == torch.float32 else 2e-2)
+    assert y.joffsets.tolist() == grid.joffsets.tolist()
+    strided = fvdb.ConvolutionPlan.from_grid_batch(2, 2, grid)
+    assert strided.target_grid_batch.grid_count == 3 and strided.target_grid_batch.num_voxels_at(1) == 0
+    # (b) every item empty
+    none = _grid(fvdb, [np.zeros((0, 3), dtype=np.int64)] * 2)
+    p0 = fvdb.ConvolutionPlan.from_grid_batch(3, 1, none, none)
+    x0 = torch.zeros((0, 32), dtype=dtype, device=DEV, requires_grad=True)
+    y0 = p0.execute(none.jagged_like(x0), w)
+    assert y0.jdata.shape == (0, 32) and p0._backend.topology.total_pairs == 0
+    gx0, gw0 = torch.autograd.grad(y0.jdata.sum(), (x0, w), allow_unused=True)
+    assert gx0.shape == (0, 32) and float(gw0.abs().sum()) == 0.0
+    # (c) one voxel: only the centre tap is live
+    one = _grid(fvdb, [[(5, -3, 2)]])
+    p1 = fvdb.ConvolutionPlan.from_grid_batch(3, 1, one, one)
+    t1 = p1._backend.topology
+    assert t1.total_pairs == 1 and t1.offsets.tolist() == [0] * 14 + [1] * 14
+    x1 = torch.arange(32, dtype=torch.float32).reshape(1, 32).to(dtype).to(DEV)
+    torch.testing.assert_close(p1.execute(x1, w).float(), (x1.float().sum() / 8).expand(1, 32), rtol=1e-2, atol=1e-2)
+    # (d) explicit target far away from the source: RESTRICTED plan with no pair; outputs are zeros, gradients are zeros
+    far = _grid(fvdb, [[(100, 100, 100), (101, 100, 100)]])
+    pd = fvdb.ConvolutionPlan.from_grid_batch(3, 1, one, far)
+    assert pd._backend.topology.total_pairs == 0
+    xd = torch.ones((1, 32), dtype=dtype, device=DEV, requires_grad=True)
+    yd = pd.execute(xd, w)
+    assert yd.shape == (2, 32) and float(yd.abs().sum()) == 0.0
+    gxd, gwd = cpp.gs_conv_backward(torch.ones_like(yd), xd.detach(), w.detach(), pd._backend.topology)
+    assert float(gxd.abs().sum()) == 0.0 and float(gwd.abs().sum()) == 0.0
+
+
+def test_full_size_properties_on_the_bench_workload(fvdb):
+    # BASELINE.json configs[1] at full size (8 indoor grids x ~200 k voxels, 3^3 64->64 bf16) through size-independent
+    # properties: map symmetry and per-grid isolation (bit-exact), all-ones == rulebook degree (exact in bf16), the adjoint
+    # identity <conv(x), d> == <x, conv^T(d)> == <W, wgrad>, linearity, and run-to-run determinism.
+    import bench
+
+    cfg = bench.CONFIGS["c2"]
+    grid = fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(bench.make_coords(cfg, 0, torch.device(DEV))))
+    n = grid.total_voxels
+    assert grid.grid_count == 8 and 8 * 190_000 <= n <= 8 * 210_000
+    plan = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid, grid)
+    topo = plan._backend.topology
+    nbr = topo._out_map()[:, :n].long()  # [27, n]
+    rows = torch.arange(n, device=DEV)
+    assert torch.equal(nbr[13], rows)  # centre tap = identity
+    for k in (0, 5, 12):  # stride-1 same grid: nbr[k][o] = i  <=>  nbr[26-k][i] = o
+        hit = nbr[k] >= 0
+        assert torch.equal(nbr[26 - k][nbr[k][hit]], rows[hit])
+    jidx = grid.jidx.long()
+    for k in (0, 9, 26):  # the map never crosses grids (GatherScatterDefault.cu:126,186-188)
+        hit = nbr[k] >= 0
+        assert torch.equal(jidx[nbr[k][hit]], jidx[hit])
+    degree = (nbr >= 0).sum(0)
+    assert int(degree.sum()) == topo.total_pairs == int(topo.offsets[-1])
+    ones_x = torch.ones((n, 64), dtype=torch.bfloat16, device=DEV)
+    ones_w = torch.full((64, 64, 3, 3, 3), 1.0 / 64, dtype=torch.bfloat16, device=DEV)
+    y = plan.execute(ones_x, ones_w) if grid.grid_count == 1 else plan.execute(grid.jagged_like(ones_x), ones_w).jdata
+    assert torch.equal(y.float(), degree.float()[:, None].expand(n, 64))  # sums <= 27 are exact in bf16
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn((n, 64), generator=gen, device=DEV).bfloat16()
+    d = torch.randn((n, 64), generator=gen, device=DEV).bfloat16()
+    w = (torch.randn((64, 64, 3, 3, 3), generator=gen, device=DEV) / 41.6).bfloat16()
+    cpp = fvdb._fvdb_cpp
+    yx = cpp.gs_conv(x, w, topo)
+    gx, gw = cpp.gs_conv_backward(d, x, w, topo)
+    lhs = float((yx.double() * d.double()).sum())
+    assert abs(lhs - float((x.double() * gx.double()).sum())) <= 2e-3 * abs(lhs)
+    assert abs(lhs - float((w.double() * gw.double()).sum())) <= 2e-3 * abs(lhs)
+    y2 = cpp.gs_conv(x, (2 * w.float()).bfloat16(), topo)  # scaling by a power of two is exact
+    assert torch.equal(y2.float(), 2 * yx.float())
+    again = cpp.gs_conv_backward(d, x, w, topo)
+    assert torch.equal(cpp.gs_conv(x, w, topo), yx) and torch.equal(again[0], gx) and torch.equal(again[1], gw)  # no atomics anywhere
