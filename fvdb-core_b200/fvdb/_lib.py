@@ -67,6 +67,9 @@ SIGNATURES = {
     "fvc_bn_backward_reduce": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.c_float, _i32, _vp, _vp, _sz, _vp]),
     "fvc_bn_backward_apply": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.c_float, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "fvc_column_sums": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fvc_pool_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp]),
+    "fvc_pool_rows_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp]),
+    "fvc_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "fvc_conv_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
 }
 

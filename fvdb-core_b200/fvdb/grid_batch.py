@@ -143,6 +143,77 @@ class GridBatch:
             return self
         return GridBatch(_fvdb_cpp.conv_transpose_grid(self.data, ks, st))
 
+    # ---- coarsening / refinement (block-centroid transforms, not the convolution lattice) --------------------------
+    def _derived(self, ijk: torch.Tensor, jidx: "torch.Tensor | None", sizes: torch.Tensor, origins: torch.Tensor) -> "GridBatch":
+        return GridBatch(_fvdb_cpp.build_grid_from_ijk(ijk, jidx if self.grid_count > 1 else None, self.grid_count, sizes, origins))
+
+    def coarsened_grid(self, coarsening_factor: NumericMaxRank1) -> "GridBatch":
+        """Coarse voxels ``floor(ijk / factor)`` (ops/BuildCoarseGridFromFine.cu:50,136); voxel size ``* factor``, origin
+        ``+ (factor - 1) * voxel_size / 2`` (detail/utils/VoxelSizeUtils.h:13-22)."""
+        f = to_Vec3i(coarsening_factor, value_constraint=ValueConstraint.POSITIVE)
+        fd = f.to(torch.float64)
+        sizes, origins = self.data.voxel_sizes.double(), self.data.origins.double()
+        coarse = torch.div(self.data.ijk, f.to(self.device, torch.int32), rounding_mode="floor").to(torch.int32)
+        return self._derived(coarse, self.data.jidx, sizes * fd, (fd - 1.0) * sizes * 0.5 + origins)
+
+    def refined_grid(self, subdiv_factor: NumericMaxRank1, mask: "JaggedTensor | torch.Tensor | None" = None) -> "GridBatch":
+        """Fine voxels ``factor * ijk + [0, factor)^3`` of every (selected) voxel (ops/BuildFineGridFromCoarse.cu); voxel size
+        ``/ factor``, origin ``- (factor - 1) * fine_voxel_size / 2`` (VoxelSizeUtils.h:24-35)."""
+        f = to_Vec3i(subdiv_factor, value_constraint=ValueConstraint.POSITIVE)
+        fd = f.to(torch.float64)
+        sizes, origins = self.data.voxel_sizes.double(), self.data.origins.double()
+        ijk, jidx = self.data.ijk, self.data.jidx
+        if mask is not None:
+            keep = (mask.jdata if isinstance(mask, JaggedTensor) else mask).to(torch.bool).reshape(-1)
+            ijk, jidx = ijk[keep], jidx[keep]
+        f0, f1, f2 = f.tolist()
+        cells = torch.stack(torch.meshgrid(torch.arange(f0), torch.arange(f1), torch.arange(f2), indexing="ij"), dim=-1).reshape(-1, 3).to(self.device, torch.int32)
+        fine = (ijk[:, None, :] * f.to(self.device, torch.int32) + cells[None]).reshape(-1, 3).contiguous()
+        return self._derived(fine, jidx.repeat_interleave(cells.shape[0]), sizes / fd, origins - (fd - 1.0) * (sizes / fd) * 0.5)
+
+    def _pool(self, mode: int, pool_factor, data: JaggedTensor, stride, coarse_grid: "GridBatch | None"):
+        from . import _pool
+
+        factor = to_Vec3i(pool_factor, value_constraint=ValueConstraint.POSITIVE).tolist()
+        st = to_Vec3i(stride, value_constraint=ValueConstraint.NON_NEGATIVE).tolist()
+        st = [s if s > 0 else f for s, f in zip(st, factor)]  # stride 0 = pool_factor (MaxPool.cu:137-140)
+        if any(s < f for s, f in zip(st, factor)):
+            raise ValueError("pooling windows must not overlap: stride >= pool_factor on every axis")
+        if coarse_grid is None:
+            coarse_grid = self.coarsened_grid(st)
+        if data.jdata.shape[0] != self.total_voxels:
+            raise ValueError("data must have one row per voxel of the fine grid")
+        idx = _pool.window_children(self, coarse_grid, factor, st)
+        scale = 1.0 if mode == _pool.POOL_MAX else 1.0 / (factor[0] * factor[1] * factor[2])  # AvgPool.cu:145: over the whole window
+        out = _pool.PoolRowsFn.apply(data.jdata, idx, mode, scale)
+        return coarse_grid.jagged_like(out), coarse_grid
+
+    def max_pool(self, pool_factor: NumericMaxRank1, data: JaggedTensor, stride: NumericMaxRank1 = 0, coarse_grid: "GridBatch | None" = None):
+        """``(pooled, coarse_grid)``: channel-wise max over the active voxels of each window (fvdb/grid_batch.py:1139-1164)."""
+        from . import _pool
+
+        return self._pool(_pool.POOL_MAX, pool_factor, data, stride, coarse_grid)
+
+    def avg_pool(self, pool_factor: NumericMaxRank1, data: JaggedTensor, stride: NumericMaxRank1 = 0, coarse_grid: "GridBatch | None" = None):
+        """``(pooled, coarse_grid)``: sum over the active voxels of each window divided by the window volume (grid_batch.py:463-490)."""
+        from . import _pool
+
+        return self._pool(_pool.POOL_SUM, pool_factor, data, stride, coarse_grid)
+
+    def refine(self, subdiv_factor: NumericMaxRank1, data: JaggedTensor, mask: "JaggedTensor | None" = None, fine_grid: "GridBatch | None" = None):
+        """``(refined, fine_grid)``: every fine voxel takes the features of ``floor(ijk / factor)`` (grid_batch.py:1474-1499)."""
+        from . import _pool
+
+        factor = to_Vec3i(subdiv_factor, value_constraint=ValueConstraint.POSITIVE).tolist()
+        if fine_grid is None:
+            fine_grid = self.refined_grid(factor, mask)
+        if data.jdata.shape[0] != self.total_voxels:
+            raise ValueError("data must have one row per voxel of the coarse grid")
+        parent = _pool.parent_rows(self, fine_grid, factor)
+        children = _pool.window_children(fine_grid, self, factor, factor)
+        out = _pool.RefineRowsFn.apply(data.jdata, parent, children)
+        return fine_grid.jagged_like(out), fine_grid
+
     # ---- lookups ----------------------------------------------------------------------------
     def _query(self, ijk: "JaggedTensor | torch.Tensor") -> JaggedTensor:
         if isinstance(ijk, torch.Tensor):

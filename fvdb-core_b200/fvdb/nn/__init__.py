@@ -1,3 +1,3 @@
-from .modules import BatchNorm, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm
+from .modules import AvgPool, BatchNorm, MaxPool, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm, UpsamplingNearest
 
-__all__ = ["BatchNorm", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm"]
+__all__ = ["AvgPool", "BatchNorm", "MaxPool", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm", "UpsamplingNearest"]

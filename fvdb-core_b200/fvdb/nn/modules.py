@@ -16,6 +16,7 @@ from torch.profiler import record_function
 
 from .. import _norm
 from ..convolution_plan import ConvolutionPlan
+from ..grid_batch import GridBatch
 from ..jagged_tensor import JaggedTensor
 from ..types import NumericMaxRank1, ValueConstraint, to_Vec3i
 
@@ -142,3 +143,47 @@ class SyncBatchNorm(BatchNorm):
         for name, child in module.named_children():
             out.add_module(name, cls.convert_sync_batchnorm(child, process_group))
         return out
+
+
+class _Pool(nn.Module):
+    def __init__(self, kernel_size: NumericMaxRank1, stride: "NumericMaxRank1 | None" = None):
+        super().__init__()
+        self._kernel_size = to_Vec3i(kernel_size, value_constraint=ValueConstraint.POSITIVE)
+        self._stride = to_Vec3i(stride, value_constraint=ValueConstraint.POSITIVE) if stride is not None else self._kernel_size
+
+    kernel_size = property(lambda self: self._kernel_size)
+    stride = property(lambda self: self._stride)
+
+    def extra_repr(self) -> str:
+        return f"kernel_size={self.kernel_size}, stride={self.stride}"
+
+
+class MaxPool(_Pool):
+    """3-D max pooling of a JaggedTensor over a GridBatch (mirror of reference fvdb/nn/modules.py:114-200)."""
+
+    def forward(self, fine_data: JaggedTensor, fine_grid: GridBatch, coarse_grid: "GridBatch | None" = None):
+        with record_function(repr(self)):
+            return fine_grid.max_pool(self.kernel_size, fine_data, stride=self.stride, coarse_grid=coarse_grid)
+
+
+class AvgPool(_Pool):
+    """3-D average pooling of a JaggedTensor over a GridBatch (mirror of reference fvdb/nn/modules.py:33-111)."""
+
+    def forward(self, fine_data: JaggedTensor, fine_grid: GridBatch, coarse_grid: "GridBatch | None" = None):
+        with record_function(repr(self)):
+            return fine_grid.avg_pool(self.kernel_size, fine_data, stride=self.stride, coarse_grid=coarse_grid)
+
+
+class UpsamplingNearest(nn.Module):
+    """Nearest-neighbour upsampling by ``scale_factor`` (mirror of reference fvdb/nn/modules.py:203-260)."""
+
+    def __init__(self, scale_factor: NumericMaxRank1):
+        super().__init__()
+        self.scale_factor = to_Vec3i(scale_factor, value_constraint=ValueConstraint.POSITIVE)
+
+    def extra_repr(self) -> str:
+        return f"scale_factor={self.scale_factor}"
+
+    def forward(self, coarse_data: JaggedTensor, coarse_grid: GridBatch, mask: "JaggedTensor | None" = None, fine_grid: "GridBatch | None" = None):
+        with record_function(repr(self)):
+            return coarse_grid.refine(self.scale_factor, coarse_data, mask, fine_grid=fine_grid)

@@ -247,6 +247,20 @@ FVC_API int fvc_bn_backward_apply(const void *dy, const void *x, int64_t n, int3
 FVC_API int fvc_column_sums(const void *x, int64_t n, int32_t channels, int32_t dtype, float *sums, void *scratch, size_t scratch_bytes,
                     fvc_stream_t stream);
 
+/* -------- pooling / refinement between a fine and a coarse grid (replaces
+ *          ops/MaxPool.cu:16-122, ops/AvgPool.cu:17-110, ops/Refine.cu:17-110 behind GridBatch.max_pool / avg_pool / refine)
+ * idx[n_out][taps] (int32, row-major): for every output row the rows of its window children in x, -1 = inactive; the
+ * host builds it with fvc_ijk_to_index.  Rows are [n][channels] in `dtype` (f16 / bf16 / f32), channels a multiple of a
+ * 16-byte vector.  mode 0: max over the children (-inf when there is none, MaxPool.cu:46); mode 1: sum * scale. */
+FVC_API int fvc_pool_rows(const void *x, const int32_t *idx, int64_t n_out, int32_t taps, int32_t channels, int32_t dtype, int32_t mode,
+                  float scale, void *y, fvc_stream_t stream);
+/* dx (zero-initialised by the caller): mode 0 routes dy[o] to the first maximal child per channel (MaxPool.cu:100-118),
+ * mode 1 writes dy[o] * scale to every child (AvgPool.cu:98-108); windows must not overlap (one writer per element). */
+FVC_API int fvc_pool_rows_backward(const void *dy, const void *x, const int32_t *idx, int64_t n_out, int32_t taps, int32_t channels,
+                           int32_t dtype, int32_t mode, float scale, void *dx, fvc_stream_t stream);
+/* y[r] = idx[r] >= 0 ? x[idx[r]] : 0  (nearest-neighbour refinement, Refine.cu:43-56) */
+FVC_API int fvc_gather_rows(const void *x, const int32_t *idx, int64_t n_out, int32_t channels, int32_t dtype, void *y, fvc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,3 +15,4 @@ container -- see ``tests/golden/make_golden.py``.  The reference's compiled impl
 """
 
 from .conv_oracle import *  # noqa: F401,F403
+from . import pool_oracle  # noqa: F401,E402  (pooling / refinement restatement; pinned against dense torch pooling in tests/test_oracle_golden.py)

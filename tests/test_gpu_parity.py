@@ -654,3 +654,80 @@ def test_full_size_properties_on_the_bench_workload(fvdb):
     assert torch.equal(y2.float(), 2 * yx.float())
     again = cpp.gs_conv_backward(d, x, w, topo)
     assert torch.equal(cpp.gs_conv(x, w, topo), yx) and torch.equal(again[0], gx) and torch.equal(again[1], gw)  # no atomics anywhere
+
+
+# ------------------------------------------------------------------ pooling / refinement
+
+
+@pytest.mark.parametrize("dtype,channels", [(torch.float32, 12), (torch.bfloat16, 32)])
+@pytest.mark.parametrize("factor", [2, (2, 3, 1)])
+def test_pool_refine_match_oracle(fvdb, dtype, channels, factor):
+    from oracle import pool_oracle as po
+
+    f = oracle.normalize_3d(factor)
+    coords = _random_batch(70, n=2500, extent=9, batches=2)
+    fine = _grid(fvdb, coords, voxel_sizes=(0.5, 1.0, 2.0), origins=(3.0, -2.0, 7.0))
+    rows, bidx = _rows(fine)
+    coarse = fine.coarsened_grid(factor)
+    crow, cb = _rows(coarse)
+    for b in range(2):  # coordinate sets, metadata
+        want = po.coarsened_ijk(rows[bidx == b], f)
+        assert sorted(map(tuple, crow[cb == b].tolist())) == sorted(map(tuple, want.tolist()))
+    ws, wo = po.coarse_metadata((0.5, 1.0, 2.0), (3.0, -2.0, 7.0), f)
+    torch.testing.assert_close(coarse.voxel_sizes.cpu().double(), torch.tensor([ws, ws])), torch.testing.assert_close(coarse.origins.cpu().double(), torch.tensor([wo, wo]))
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn((fine.total_voxels, channels), generator=gen).to(dtype)
+    dy = torch.randn((coarse.total_voxels, channels), generator=gen).to(dtype)
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    for mode, fn in (("max", fine.max_pool), ("avg", fine.avg_pool)):
+        xd = x.to(DEV).requires_grad_()
+        y, cg = fn(factor, fine.jagged_like(xd))
+        assert cg.total_voxels == coarse.total_voxels and y.jdata.dtype == dtype
+        want_y, children = po.pool(rows, bidx, x.double().numpy(), crow, cb, f, (0, 0, 0), mode)
+        assert _rel_err(y.jdata.detach(), torch.from_numpy(want_y).float()) <= tol
+        (gx,) = torch.autograd.grad(y.jdata, xd, dy.to(DEV))
+        want_gx = po.pool_backward(dy.double().numpy(), x.double().numpy(), children, len(rows), mode)
+        assert _rel_err(gx, torch.from_numpy(want_gx).float()) <= tol
+        y2, _ = fn(factor, fine.jagged_like(xd), coarse_grid=coarse)  # explicit coarse grid: same rows
+        assert torch.equal(y2.jdata, y.jdata)
+    # refine back onto the original fine grid, and onto the generated refined grid
+    z = torch.randn((coarse.total_voxels, channels), generator=gen).to(dtype)
+    zd = z.to(DEV).requires_grad_()
+    up, fg = coarse.refine(factor, coarse.jagged_like(zd), fine_grid=fine)
+    want_up, parent = po.refine(crow, cb, z.double().numpy(), rows, bidx, f)
+    assert fg.is_same(fine) and (parent >= 0).all() and _rel_err(up.jdata.detach(), torch.from_numpy(want_up).float()) <= tol
+    dup = torch.randn((fine.total_voxels, channels), generator=gen).to(dtype)
+    (gz,) = torch.autograd.grad(up.jdata, zd, dup.to(DEV))
+    assert _rel_err(gz, torch.from_numpy(po.refine_backward(dup.double().numpy(), parent, len(crow))).float()) <= tol
+    refined = coarse.refined_grid(factor)
+    rrow, rb = _rows(refined)
+    for b in range(2):
+        want = po.refined_ijk(crow[cb == b], f)
+        assert sorted(map(tuple, rrow[rb == b].tolist())) == sorted(map(tuple, want.tolist()))
+    fs, fo = po.fine_metadata(ws, wo, f)
+    torch.testing.assert_close(refined.voxel_sizes.cpu().double(), torch.tensor([fs, fs])), torch.testing.assert_close(refined.origins.cpu().double(), torch.tensor([fo, fo]))
+    masked = coarse.refined_grid(factor, mask=coarse.jagged_like(torch.arange(coarse.total_voxels, device=DEV) % 2 == 0))
+    assert masked.total_voxels == ((coarse.total_voxels + 1) // 2) * f[0] * f[1] * f[2]
+    with pytest.raises(ValueError, match="must not overlap"):
+        fine.max_pool(3, fine.jagged_like(x.to(DEV)), stride=2)
+
+
+def test_nn_pooling_modules_and_unet_style_block(fvdb):
+    # MaxPool -> 1x1x1 conv -> BatchNorm(+ReLU) -> UpsamplingNearest, the down / up pattern of the reference's SimpleUNet
+    # (fvdb/nn/simple_unet.py:194-294), trained for one step.
+    fine = _grid(fvdb, _random_batch(90, n=4000, extent=12, batches=2))
+    coarse = fine.coarsened_grid(2)
+    pool, up = fvdb.nn.MaxPool(2), fvdb.nn.UpsamplingNearest(2)
+    fan_out = fvdb.nn.SparseConv3d(16, 32, kernel_size=1, bias=False).to(DEV)
+    norm = fvdb.nn.BatchNorm(32, activation="relu").to(DEV)
+    plan = fvdb.ConvolutionPlan.from_grid_batch(1, 1, coarse, coarse)
+    x = fine.jagged_like(torch.randn((fine.total_voxels, 16), device=DEV, requires_grad=True))
+    pooled, cg = pool(x, fine, coarse)
+    assert cg.is_same(coarse) and pooled.jdata.shape == (coarse.total_voxels, 16)
+    h = norm(fan_out(pooled, plan), coarse)
+    out, fg = up(h, coarse, fine_grid=fine)
+    assert fg.is_same(fine) and out.jdata.shape == (fine.total_voxels, 32)
+    out.jdata.square().mean().backward()
+    assert torch.isfinite(x.jdata.grad).all() and float(fan_out.weight.grad.abs().sum()) > 0 and float(norm.weight.grad.abs().sum()) > 0
+    avg, _ = fvdb.nn.AvgPool(2)(x, fine)
+    assert avg.jdata.shape == (coarse.total_voxels, 16)

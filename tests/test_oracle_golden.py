@@ -250,3 +250,49 @@ def test_half_promotion_and_empty():
     assert oracle.gs_conv(torch.zeros(0, 4), w, empty).shape == (0, 4)
     gf, gw = oracle.gs_conv_backward(torch.zeros(0, 4), torch.zeros(0, 4), w, empty)
     assert gf.shape == (0, 4) and gw.shape == w.shape and not gw.any()
+
+
+# ------------------------------------------------------------------ pooling / refinement oracle
+
+
+def test_pool_oracle_matches_dense_torch_pooling():
+    # On a dense block the sparse definitions must equal torch's dense pooling / nearest upsampling (what the reference's own
+    # tests compare against); this pins oracle/pool_oracle.py.
+    from oracle import pool_oracle as po
+
+    rng = np.random.default_rng(0)
+    dim, c = 8, 5
+    ijk = np.stack(np.meshgrid(np.arange(dim), np.arange(dim), np.arange(dim), indexing="ij"), -1).reshape(-1, 3)
+    bidx = np.zeros(len(ijk), dtype=np.int64)
+    x = rng.standard_normal((len(ijk), c))
+    dense = torch.from_numpy(x.reshape(dim, dim, dim, c)).permute(3, 0, 1, 2)[None]
+    for factor in ((2, 2, 2), (2, 4, 1)):
+        coarse = po.coarsened_ijk(ijk, factor)
+        assert len(coarse) == (dim // factor[0]) * (dim // factor[1]) * (dim // factor[2])
+        cb = np.zeros(len(coarse), dtype=np.int64)
+        for mode, fn in (("max", torch.nn.functional.max_pool3d), ("avg", torch.nn.functional.avg_pool3d)):
+            y, children = po.pool(ijk, bidx, x, coarse, cb, factor, (0, 0, 0), mode)
+            want = fn(dense, kernel_size=factor)[0].permute(1, 2, 3, 0).numpy()
+            got = np.zeros_like(want)
+            got[coarse[:, 0], coarse[:, 1], coarse[:, 2]] = y
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+            assert (children >= 0).all()
+        up, parent = po.refine(coarse, cb, y, ijk, bidx, factor)
+        np.testing.assert_array_equal(up, y[parent])
+        dxs = po.refine_backward(np.ones_like(up), parent, len(coarse))
+        assert (dxs == factor[0] * factor[1] * factor[2]).all()
+        fine_again = po.refined_ijk(coarse, factor)
+        assert sorted(map(tuple, fine_again.tolist())) == sorted(map(tuple, ijk.tolist()))
+    # metadata: block-centroid transforms are mutually inverse
+    s, o = po.coarse_metadata((0.5, 1.0, 2.0), (3.0, -2.0, 7.0), (2, 3, 4))
+    s2, o2 = po.fine_metadata(s, o, (2, 3, 4))
+    np.testing.assert_allclose(s2, (0.5, 1.0, 2.0)), np.testing.assert_allclose(o2, (3.0, -2.0, 7.0))
+    # max backward on a sparse signed set: the gradient goes to the first maximal child only
+    pts = np.array([[-1, 0, 0], [-2, 0, 0], [0, 0, 0], [5, 5, 5]])
+    xv = np.array([[1.0], [3.0], [2.0], [7.0]])
+    coarse = po.coarsened_ijk(pts, (2, 2, 2))
+    assert sorted(map(tuple, coarse.tolist())) == [(-1, 0, 0), (0, 0, 0), (2, 2, 2)]
+    y, children = po.pool(pts, np.zeros(4, dtype=np.int64), xv, coarse, np.zeros(3, dtype=np.int64), (2, 2, 2), (0, 0, 0), "max")
+    assert y[:, 0].tolist() == [3.0, 2.0, 7.0]
+    dx = po.pool_backward(np.array([[10.0], [20.0], [30.0]]), xv, children, 4, "max")
+    assert dx[:, 0].tolist() == [0.0, 10.0, 20.0, 30.0]
