@@ -65,7 +65,10 @@ template <> struct PoolVec<__half> {
     }
 };
 
-// y[o] = reduce over taps t with idx[o][t] >= 0 of x[idx[o][t]]  (max: -inf when no child, as MaxPool.cu:46; sum scaled)
+// y[o] = reduce over taps t with idx[o][t] >= 0 of x[idx[o][t]]  (sum: scaled).  A window without any active child yields
+// ZERO: that is the documented contract of MaxPool (fvdb/nn/modules.py:125-128 "not covered by any source voxels ... set to
+// zero"); the reference kernel itself leaves its -INFINITY initialiser there (MaxPool.cu:46), which poisons every network
+// that pools onto a dilated coarse grid (fvdb/nn/simple_unet.py:433).
 template <typename T>
 __global__ void __launch_bounds__(POOL_THREADS)
 pool_rows_kernel(const T *__restrict__ x, const int32_t *__restrict__ idx, int64_t n_out, int taps, int c, int mode, float scale,
@@ -80,15 +83,22 @@ pool_rows_kernel(const T *__restrict__ x, const int32_t *__restrict__ idx, int64
 #pragma unroll
         for (int i = 0; i < V; ++i)
             acc[i] = mode == POOL_MAX ? -INFINITY : 0.f;
+        bool any = false;
         for (int t = 0; t < taps; ++t) {
             const int r = __ldg(idx + o * taps + t);
             if (r < 0)
                 continue;
+            any = true;
             float v[V];
             PoolVec<T>::load(x + int64_t(r) * c + col, v);
 #pragma unroll
             for (int i = 0; i < V; ++i)
                 acc[i] = mode == POOL_MAX ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+        }
+        if (!any) {
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                acc[i] = 0.f;
         }
         if (mode == POOL_SUM) {
 #pragma unroll

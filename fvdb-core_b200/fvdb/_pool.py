@@ -20,11 +20,23 @@ POOL_MAX, POOL_SUM = 0, 1
 def _check_rows(x: torch.Tensor, what: str) -> None:
     if not x.is_cuda:
         raise RuntimeError(f"{what}: this build runs on CUDA (sm_100a) only; got device {x.device}")
-    if x.dim() != 2 or x.dtype not in _CODES:
-        raise RuntimeError(f"{what}: data must be [N, C] in float16 / bfloat16 / float32, got {tuple(x.shape)} {x.dtype}")
-    vec = 4 if x.dtype == torch.float32 else 8
-    if x.shape[1] % vec:
-        raise RuntimeError(f"{what}: the channel count must be a multiple of {vec} for {x.dtype}, got {x.shape[1]}")
+    if x.dim() != 2:
+        raise RuntimeError(f"{what}: data must be [N, C], got {tuple(x.shape)}")
+
+
+def _native(x: torch.Tensor) -> bool:
+    """Row kernels serve f16 / bf16 / f32 with whole 16-byte channel vectors; other shapes (e.g. the 3- or 5-channel ends
+    of a network, fp64) go through torch index ops on the same child tables."""
+    return x.dtype in _CODES and x.shape[1] % (4 if x.dtype == torch.float32 else 8) == 0 and x.shape[1] > 0
+
+
+def _pool_torch(x, idx, mode, scale):
+    live = idx >= 0
+    rows = x[idx.clamp_min(0).long()]  # [n_out, taps, C]
+    if mode == POOL_MAX:
+        y = rows.masked_fill(~live[:, :, None], float("-inf")).amax(dim=1)
+        return torch.where(live.any(dim=1, keepdim=True), y, torch.zeros_like(y))
+    return (rows * live[:, :, None]).sum(dim=1) * scale
 
 
 def window_children(fine, coarse, factor: list[int], stride: list[int]) -> torch.Tensor:
@@ -54,7 +66,6 @@ def _stream(x):
 class PoolRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, idx, mode, scale):  # type: ignore[override]
-        _check_rows(x, "pool")
         x = x.contiguous()
         n_out, taps = idx.shape
         y = torch.empty((n_out, x.shape[1]), dtype=x.dtype, device=x.device)
@@ -81,7 +92,6 @@ class RefineRowsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, parent, children):  # type: ignore[override]
-        _check_rows(x, "refine")
         x = x.contiguous()
         y = torch.empty((parent.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
@@ -98,3 +108,15 @@ class RefineRowsFn(torch.autograd.Function):
             check(lib.fvc_pool_rows(dy.data_ptr(), children.data_ptr(), children.shape[0], children.shape[1], dy.shape[1], _CODES[dy.dtype], POOL_SUM, 1.0,
                                     dx.data_ptr(), _stream(dy)))
         return dx, None, None
+
+
+def pool_rows(x: torch.Tensor, idx: torch.Tensor, mode: int, scale: float) -> torch.Tensor:
+    _check_rows(x, "pool")
+    return PoolRowsFn.apply(x, idx, mode, scale) if _native(x) else _pool_torch(x, idx, mode, scale)
+
+
+def refine_rows(x: torch.Tensor, parent: torch.Tensor, children: torch.Tensor) -> torch.Tensor:
+    _check_rows(x, "refine")
+    if _native(x):
+        return RefineRowsFn.apply(x, parent, children)
+    return x[parent.clamp_min(0).long()] * (parent >= 0)[:, None]

@@ -185,7 +185,7 @@ class GridBatch:
             raise ValueError("data must have one row per voxel of the fine grid")
         idx = _pool.window_children(self, coarse_grid, factor, st)
         scale = 1.0 if mode == _pool.POOL_MAX else 1.0 / (factor[0] * factor[1] * factor[2])  # AvgPool.cu:145: over the whole window
-        out = _pool.PoolRowsFn.apply(data.jdata, idx, mode, scale)
+        out = _pool.pool_rows(data.jdata, idx, mode, scale)
         return coarse_grid.jagged_like(out), coarse_grid
 
     def max_pool(self, pool_factor: NumericMaxRank1, data: JaggedTensor, stride: NumericMaxRank1 = 0, coarse_grid: "GridBatch | None" = None):
@@ -211,7 +211,7 @@ class GridBatch:
             raise ValueError("data must have one row per voxel of the coarse grid")
         parent = _pool.parent_rows(self, fine_grid, factor)
         children = _pool.window_children(fine_grid, self, factor, factor)
-        out = _pool.RefineRowsFn.apply(data.jdata, parent, children)
+        out = _pool.refine_rows(data.jdata, parent, children)
         return fine_grid.jagged_like(out), fine_grid
 
     # ---- lookups ----------------------------------------------------------------------------

@@ -1,3 +1,18 @@
 from .modules import AvgPool, BatchNorm, MaxPool, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm, UpsamplingNearest
+from .simple_unet import (
+    SimpleUNet,
+    SimpleUNetBasicBlock,
+    SimpleUNetBottleneck,
+    SimpleUNetConvBlock,
+    SimpleUNetDown,
+    SimpleUNetDownUp,
+    SimpleUNetPad,
+    SimpleUNetUnpad,
+    SimpleUNetUp,
+)
 
-__all__ = ["AvgPool", "BatchNorm", "MaxPool", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm", "UpsamplingNearest"]
+__all__ = [
+    "AvgPool", "BatchNorm", "MaxPool", "SimpleUNet", "SimpleUNetBasicBlock", "SimpleUNetBottleneck", "SimpleUNetConvBlock", "SimpleUNetDown",
+    "SimpleUNetDownUp", "SimpleUNetPad", "SimpleUNetUnpad", "SimpleUNetUp", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm",
+    "UpsamplingNearest",
+]

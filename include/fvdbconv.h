@@ -251,7 +251,8 @@ FVC_API int fvc_column_sums(const void *x, int64_t n, int32_t channels, int32_t 
  *          ops/MaxPool.cu:16-122, ops/AvgPool.cu:17-110, ops/Refine.cu:17-110 behind GridBatch.max_pool / avg_pool / refine)
  * idx[n_out][taps] (int32, row-major): for every output row the rows of its window children in x, -1 = inactive; the
  * host builds it with fvc_ijk_to_index.  Rows are [n][channels] in `dtype` (f16 / bf16 / f32), channels a multiple of a
- * 16-byte vector.  mode 0: max over the children (-inf when there is none, MaxPool.cu:46); mode 1: sum * scale. */
+ * 16-byte vector.  mode 0: max over the children (0 when there is none: the documented contract, fvdb/nn/modules.py:125-128;
+ * the reference kernel leaves -inf there, MaxPool.cu:46); mode 1: sum * scale. */
 FVC_API int fvc_pool_rows(const void *x, const int32_t *idx, int64_t n_out, int32_t taps, int32_t channels, int32_t dtype, int32_t mode,
                   float scale, void *y, fvc_stream_t stream);
 /* dx (zero-initialised by the caller): mode 0 routes dy[o] to the first maximal child per channel (MaxPool.cu:100-118),

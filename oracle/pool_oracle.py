@@ -7,7 +7,9 @@ Follows, per function:
   refined_ijk        ops/BuildFineGridFromCoarse.cu            fine = factor * coarse + [0, factor)^3
   coarse/fine metadata  detail/utils/VoxelSizeUtils.h:13-35
   max_pool / avg_pool   ops/MaxPool.cu:16-63,65-122; ops/AvgPool.cu:17-65,67-110,145  (window = stride * c + [0, factor)^3;
-                        max over ACTIVE children, -inf if none; avg = sum over active children / window volume;
+                        max over ACTIVE children; a window with no active child gives 0 (the documented contract,
+                        fvdb/nn/modules.py:125-128 -- the kernel's own -inf initialiser, MaxPool.cu:46, is a reference
+                        defect this build does not reproduce); avg = sum over active children / window volume;
                         max backward: first maximal child takes the gradient)
   refine             ops/Refine.cu:17-58                        fine takes floor(fine / factor)'s features if that voxel is active
 Parity: these are plain definitions; the reference's tests for them (tests/unit/test_basic_ops.py max_pool / refine cases)
@@ -62,6 +64,7 @@ def pool(fine_ijk, fine_bidx, x, coarse_ijk, coarse_bidx, factor, stride, mode: 
                 y[r] = np.maximum(y[r], x[lut[key]]) if mode == "max" else y[r] + x[lut[key]]
     if mode == "avg":
         y /= float(len(cells))
+    y[(children < 0).all(axis=1)] = 0.0
     return y, children
 
 

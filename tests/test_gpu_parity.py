@@ -731,3 +731,29 @@ def test_nn_pooling_modules_and_unet_style_block(fvdb):
     assert torch.isfinite(x.jdata.grad).all() and float(fan_out.weight.grad.abs().sum()) > 0 and float(norm.weight.grad.abs().sum()) > 0
     avg, _ = fvdb.nn.AvgPool(2)(x, fine)
     assert avg.jdata.shape == (coarse.total_voxels, 16)
+
+
+@pytest.mark.parametrize("dtype,widths", [(torch.float32, (3, 4, 5)), (torch.bfloat16, (8, 16, 8))])
+def test_simple_unet_forward_backward(fvdb, dtype, widths):
+    # The reference's own SimpleUNet checks (tests/unit/test_simple_unet.py:33-160): dense 16^3 block plus a sparse second
+    # grid, finite outputs of the right shape, finite gradients for every parameter, reference-compatible state_dict keys.
+    cin, base, cout = widths
+    dense = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(-1, 3)
+    grid = _grid(fvdb, [dense, _random_batch(33, n=1500, extent=7, batches=1)[0]])
+    torch.manual_seed(42)
+    model = fvdb.nn.SimpleUNet(cin, base, cout, channel_growth_rate=2, kernel_size=3, downup_layer_count=2, block_layer_count=1).to(DEV).to(dtype)
+    keys = set(model.state_dict())
+    for expected in ("pad.conv.weight", "pad.batch_norm.running_var", "downup.conv_in.blocks.0.conv.weight", "downup.down.channel_fan_out.weight",
+                     "downup.inner.down.batch_norm.weight", "downup.inner.inner.block.blocks.0.batch_norm.bias", "downup.inner.up.channel_fan_in.weight",
+                     "downup.up.batch_norm.num_batches_tracked", "downup.conv_out.blocks.0.conv.weight", "unpad.deconv.weight"):
+        assert expected in keys
+    assert model.downup.down.channel_fan_out.weight.shape == (2 * base, base) and model.unpad.deconv.weight.shape == (cout, base, 3, 3, 3)
+    x = grid.jagged_like(torch.randn((grid.total_voxels, cin), device=DEV).to(dtype))
+    out = model(x, grid)
+    assert out.jdata.shape == (grid.total_voxels, cout) and out.jdata.dtype == dtype and torch.isfinite(out.jdata).all()
+    out.jdata.float().sum().backward()
+    for name, param in model.named_parameters():
+        assert param.grad is not None and torch.isfinite(param.grad).all(), name
+    single = fvdb.nn.SimpleUNet(cin, base, cout, 2, downup_layer_count=1, block_layer_count=2).to(DEV).to(dtype)
+    with torch.no_grad():
+        assert torch.isfinite(single(x, grid).jdata).all()
