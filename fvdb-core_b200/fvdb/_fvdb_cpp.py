@@ -181,13 +181,56 @@ def build_grid_from_ijk(ijk: torch.Tensor, jidx: "torch.Tensor | None", num_grid
     )
 
 
+_LEAF_NEIGHBOURS = torch.tensor([[dx, dy, dz] for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)], dtype=torch.int32) * 8
+use_leaf_morphology = True  # tests switch this off to cross-check the fast path against the candidate path
+
+
+def _dilated_grid(grid: GridBatchData, lo: list[int], hi: list[int], voxel_sizes: torch.Tensor, origins: torch.Tensor) -> GridBatchData:
+    """out(c) = OR over o in [lo, hi]^3 of grid(c - o), by leaf-mask morphology (csrc/grid_morph.cu): the neighbour-leaf origins
+    (27 keys per LEAF) go through the ordinary builder, one warp per output leaf dilates the 3x3x3 source masks, a scan of the
+    leaf counts gives the row bases.  One extra count read-back."""
+    device = grid.device
+    words = grid.leaves.view(torch.int32).reshape(-1, 32)  # FvcLeaf: mask 16 | prefix 4 | base | batch | origin[3] | count | ...
+    origin, batch = words[:, 22:25], words[:, 21]
+    near = [o for o in _LEAF_NEIGHBOURS.tolist() if all((d == 0) or (d < 0 and l < 0) or (d > 0 and h > 0) for d, l, h in zip(o, lo, hi))]
+    near_t = torch.tensor(near, dtype=torch.int32, device=device)
+    cand = (origin[:, None, :] + near_t[None]).reshape(-1, 3)
+    skeleton = build_grid_from_ijk(cand, batch.repeat_interleave(len(near)), grid.num_grids, voxel_sizes, origins)
+    nl = skeleton.num_leaves
+    with torch.cuda.device(device):
+        stream = _stream(device)
+        counts = torch.empty(nl, dtype=torch.int32, device=device)
+        check(lib.fvc_grid_dilate_leaves(grid.struct, _ptr(skeleton.leaves), nl, i3(lo), i3(hi), _ptr(counts), stream))
+        ends = torch.cumsum(counts, 0, dtype=torch.int64)
+        total = int(ends[-1]) if nl else 0  # the read-back that sizes the voxel list
+        if total > _INT32_MAX:
+            raise RuntimeError(f"generated topology would hold {total} voxels, exceeding the int32 limit")
+        base = (ends - counts).to(torch.int32)
+        out_ijk = torch.empty((total, 3), dtype=torch.int32, device=device)
+        out_jidx = torch.empty(total, dtype=torch.int32, device=device)
+        check(lib.fvc_grid_expand_leaves(_ptr(skeleton.leaves), nl, _ptr(base), _ptr(out_ijk), _ptr(out_jidx), stream))
+        ends0 = torch.cat([ends.new_zeros(1), ends])
+        voxel_offsets = ends0[skeleton.leaf_offsets.long()].contiguous()
+    return GridBatchData(
+        device=device, num_grids=grid.num_grids, counts=(total, nl, skeleton.num_lower, skeleton.num_upper), leaves=skeleton.leaves,
+        lower=skeleton.lower, upper=skeleton.upper, root_keys=skeleton.root_keys, root_offsets=skeleton.root_offsets, voxel_offsets=voxel_offsets,
+        leaf_offsets=skeleton.leaf_offsets, ijk=out_ijk, jidx=out_jidx, voxel_sizes=voxel_sizes, origins=origins,
+    )
+
+
 def _generated_grid(grid: GridBatchData, kernel_size, stride, transposed: bool) -> GridBatchData:
     ks, st = _vec3(kernel_size), _vec3(stride)
-    ConvolutionGeometry(ks, st)  # validation (ValueError on non-positive sizes)
+    geometry = ConvolutionGeometry(ks, st)  # validation (ValueError on non-positive sizes)
     device = grid.device
     _require_cuda(device, "conv_grid")
     scale = torch.tensor(st, dtype=torch.float64)
     voxel_sizes = grid.voxel_sizes / scale if transposed else grid.voxel_sizes * scale  # BuildGridForConv.cu:533-538, Transpose :350-355
+    if use_leaf_morphology and st == [1, 1, 1] and max(ks) <= 8 and grid.total_voxels > 0:
+        # stride 1: the support is a box dilation.  forward: coarse = fine - tap + pad; transposed: fine = coarse + tap - pad
+        pad = geometry.padding_before
+        lo = [-p for p in pad] if transposed else [p - (k - 1) for p, k in zip(pad, ks)]
+        hi = [k - 1 - p for p, k in zip(pad, ks)] if transposed else list(pad)
+        return _dilated_grid(grid, lo, hi, voxel_sizes, grid.origins.clone())
     with torch.cuda.device(device):
         stream = _stream(device)
         n = grid.total_voxels

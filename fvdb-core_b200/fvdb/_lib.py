@@ -49,6 +49,8 @@ SIGNATURES = {
     "fvc_grid_build_fill": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _sz, C.POINTER(_i64 * 4)] + [_vp] * 9 + [_vp]),
     "fvc_conv_grid_count": (C.c_int, [_vp, _i64, _I3, _I3, _i32, _vp, C.POINTER(_i64), _vp]),
     "fvc_conv_grid_emit": (C.c_int, [_vp, _vp, _i64, _I3, _I3, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "fvc_grid_dilate_leaves": (C.c_int, [_GB, _vp, _i32, _I3, _I3, _vp, _vp]),
+    "fvc_grid_expand_leaves": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "fvc_kmap_build": (C.c_int, [_GB, _GB, _I3, _I3, _i32, _vp, _i64, _vp, _vp]),
     "fvc_kmap_csr_scratch_bytes": (_sz, [_i64, _i64]),
     "fvc_kmap_to_csr": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -221,6 +221,18 @@ FVC_API int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather,
                    int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, void *grad_w,
                    void *scratch, size_t scratch_bytes, fvc_stream_t stream);
 
+/* -------- stride-1 generated topologies by leaf-mask morphology (fast path of conv_grid / conv_transpose_grid;
+ *          replaces the NanoVDB DilateGrid route of ops/BuildGridForConv.cu:392-463) --------------------------------
+ * dst_leaves: the leaves of a grid whose tree already holds every leaf the result can touch (built by the ordinary
+ * grid builder from the neighbour-leaf origins of `src`); their masks / prefixes / counts are overwritten with
+ * out(c) = OR over o in [lo, hi]^3 of src(c - o), |o| < 8; leaf_counts[n] receives the voxel count of every leaf. */
+FVC_API int fvc_grid_dilate_leaves(const FvcGridBatch *src, FvcLeaf *dst_leaves, int32_t n_dst_leaves, const int32_t lo[3],
+                           const int32_t hi[3], int32_t *leaf_counts, fvc_stream_t stream);
+/* leaf_base[n] (exclusive scan of the counts, batch-cumulative) -> leaf records, voxel list out_ijk [rows][3] and grid
+ * index out_bidx [rows] in row order */
+FVC_API int fvc_grid_expand_leaves(FvcLeaf *leaves, int32_t n_leaves, const int32_t *leaf_base, int32_t *out_ijk, int32_t *out_bidx,
+                           fvc_stream_t stream);
+
 /* -------- normalisation around the convolution (replaces torch.nn.BatchNorm1d over jdata
  *          + the separate ReLU pass of fvdb/nn/modules.py:484-521,91-110 and the bias-gradient reduction) -------------
  * Rows are [n][channels] row-major in `dtype` (f16 / bf16 / f32), channels a multiple of 16 bytes' worth of elements.

@@ -757,3 +757,29 @@ def test_simple_unet_forward_backward(fvdb, dtype, widths):
     single = fvdb.nn.SimpleUNet(cin, base, cout, 2, downup_layer_count=1, block_layer_count=2).to(DEV).to(dtype)
     with torch.no_grad():
         assert torch.isfinite(single(x, grid).jdata).all()
+
+
+@pytest.mark.parametrize("ks", [2, 3, 5, (3, 5, 7), 8, (1, 4, 2)])
+def test_stride1_leaf_morphology_equals_candidate_path(fvdb, ks):
+    # conv_grid / conv_transpose_grid at stride 1 by leaf-mask dilation (csrc/grid_morph.cu) == the sort-unique candidate path,
+    # voxel for voxel and row for row; the rebuilt leaves answer lookups consistently (ijk_to_index o ijk == identity).
+    cpp = fvdb._fvdb_cpp
+    from fvdb.utils.synthetic import sphere_shell
+
+    coords = [sphere_shell(target=5000, domain=64, seed=5, device="cpu").numpy() - 30, _random_batch(61, n=2500, extent=25, batches=1)[0],
+              np.array([[4095, 4095, 4095], [4096, 4096, 4096], [-4097, 7, 8], [-1, -1, -1]])]  # straddles root tiles
+    grid = _grid(fvdb, coords)
+    for fn in (grid.conv_grid, grid.conv_transpose_grid):
+        try:
+            cpp.use_leaf_morphology = False
+            want = fn(ks, 1)
+        finally:
+            cpp.use_leaf_morphology = True
+        got = fn(ks, 1)
+        assert torch.equal(got.ijk.jdata, want.ijk.jdata) and torch.equal(got.jidx, want.jidx) and torch.equal(got.joffsets, want.joffsets)
+        idx = got.ijk_to_index(got.ijk, cumulative=True).jdata
+        assert torch.equal(idx, torch.arange(got.total_voxels, device=DEV))
+        probe = got.ijk.jdata + torch.tensor([[0, 0, 9]], device=DEV, dtype=torch.int32)  # mostly outside: agree with the reference build
+        assert torch.equal(got.ijk_to_index(got.jagged_like(probe)).jdata, want.ijk_to_index(want.jagged_like(probe)).jdata)
+    plan = fvdb.ConvolutionPlan.from_grid_batch(3, 1, grid)  # target generated by the fast path
+    assert plan._backend.topology.total_pairs == 27 * grid.total_voxels  # complete support: every tap of every voxel lands
