@@ -339,29 +339,47 @@ __global__ void conv_grid_count_kernel(const int32_t *__restrict__ ijk, int64_t 
 }
 
 // forward: each fine voxel emits floorDiv(fine - tap + pad, S) for every divisible tap
-// (BuildGridForConv.cu:485-510); candidates are claimed with one atomic per voxel (order is irrelevant,
+// (BuildGridForConv.cu:485-510); candidates are claimed with one aggregated atomic per warp (order is irrelevant,
 // the grid builder sorts and de-duplicates).
 __global__ void conv_grid_emit_fwd_kernel(const int32_t *__restrict__ ijk, const int32_t *__restrict__ bidx, int64_t n,
                                           Geometry g, int64_t capacity, int32_t *__restrict__ cand_ijk,
                                           int32_t *__restrict__ cand_bidx, unsigned long long *__restrict__ counter) {
-    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        const int c[3] = {ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]};
-        int r[3], m[3];
+    const int lane = threadIdx.x & 31;
+    // warp-uniform loop; one aggregated atomic per warp claims the candidates of its 32 voxels
+    for (int64_t i0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x - lane; i0 < n; i0 += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const bool valid = i < n;
+        int c[3] = {0, 0, 0}, r[3] = {0, 0, 0}, m[3] = {0, 0, 0};
+        if (valid) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            r[d] = floor_mod(c[d] + g.pad[d], g.s[d]); // smallest admissible tap
-            m[d] = divisible_taps(c[d], g.k[d], g.s[d], g.pad[d]);
+            for (int d = 0; d < 3; ++d) {
+                c[d] = ijk[3 * i + d];
+                r[d] = floor_mod(c[d] + g.pad[d], g.s[d]); // smallest admissible tap
+                m[d] = divisible_taps(c[d], g.k[d], g.s[d], g.pad[d]);
+            }
         }
         const int total = m[0] * m[1] * m[2];
+        int incl = total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d)
+                incl += v;
+        }
+        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long warp_base = 0ull;
+        if (lane == 0 && warp_total > 0)
+            warp_base = atomicAdd(counter, (unsigned long long)warp_total);
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
         if (total == 0)
             continue;
-        int64_t pos = int64_t(atomicAdd(counter, (unsigned long long)total));
+        int64_t pos = int64_t(warp_base) + incl - total;
         const int b = bidx ? bidx[i] : 0;
         for (int a = 0; a < m[0]; ++a)
             for (int bb = 0; bb < m[1]; ++bb)
                 for (int cc = 0; cc < m[2]; ++cc, ++pos) {
                     if (pos >= capacity)
-                        return;
+                        break;
                     cand_ijk[3 * pos] = floor_div(c[0] - (r[0] + a * g.s[0]) + g.pad[0], g.s[0]);
                     cand_ijk[3 * pos + 1] = floor_div(c[1] - (r[1] + bb * g.s[1]) + g.pad[1], g.s[1]);
                     cand_ijk[3 * pos + 2] = floor_div(c[2] - (r[2] + cc * g.s[2]) + g.pad[2], g.s[2]);
