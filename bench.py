@@ -224,7 +224,7 @@ def run_ours(args, cfg):
     t0 = time.perf_counter()
     plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid)
     topo = plan._backend.topology
-    topo._in_map()  # reversed dense map for dgrad is part of the (amortised) plan
+    topo._dgrad_plan()  # the input-stationary map for dgrad is part of the (amortised) plan (a symmetric map serves as it is)
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
     n, P, k3 = grid.total_voxels, topo.total_pairs, topo.kernel_volume
@@ -289,11 +289,12 @@ def run_ours(args, cfg):
 
     code = cpp._DTYPE_CODE[dtype]
     w_fwd = cpp._pack_weights(w, dtype, 0)
-    w_bwd = cpp._pack_weights(w, dtype, 1)
-    out_map, in_map = topo._out_map(), topo._in_map()
+    in_map, in_mask, mirror = topo._dgrad_plan()
+    w_bwd = cpp._pack_weights(w, dtype, 1, flip_taps=mirror)
+    out_map = topo._out_map()
     kern_ms = {
         "fwd": timed(lambda: cpp._run_conv(x, w_fwd, out_map, n, n, cin, cout, k3, None, topo._out_mask()), max(3, args.steps)),
-        "dgrad": timed(lambda: cpp._run_conv(dy, w_bwd, in_map, n, n, cout, cin, k3, None, topo._in_mask()), max(3, args.steps)),
+        "dgrad": timed(lambda: cpp._run_conv(dy, w_bwd, in_map, n, n, cout, cin, k3, None, in_mask), max(3, args.steps)),
     }
     kern_ms["wgrad"] = max(bwd_ms - kern_ms["dgrad"], 1e-6)  # (with N > 1 this includes the un-overlapped tail of the all-reduce)
     peaks = load_peaks()
@@ -375,6 +376,20 @@ def run_ours(args, cfg):
     barrier()
     e2e_ms = a.elapsed_time(b) / args.steps
 
+    # the e2e number is bound by the host link: report what this box's link does on a plain pinned copy of the same buffers
+    def link_gbps(dst, src):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        p0, p1 = ev(), ev()
+        p0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        return src.numel() * src.element_size() * 3 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+
+    link = {"h2d_GBps": round(link_gbps(x, x_host), 1), "d2h_GBps": round(link_gbps(y_host, x), 1)}
+
     stats = torch.tensor([ms, e2e_ms, float(n), float(P)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
@@ -407,7 +422,7 @@ def run_ours(args, cfg):
             "roofline_step": {"roofline_ms": roof_time * 1e3, "measured_ms": fwd_ms + bwd_ms, "frac": roof_time * 1e3 / (fwd_ms + bwd_ms)},
             "phase_ms": {"fwd": fwd_ms, "dgrad+wgrad": bwd_ms},
             "cpu_baseline": cpu,
-            "e2e": {"value": total_n / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms, "mode": e2e_mode,
+            "e2e": {"value": total_n / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms, "mode": e2e_mode, "host_link_probe": link,
                     "h2d_bytes_per_step": int(x_host.numel() * s + dy_host.numel() * s), "d2h_bytes_per_step": int((y_host.numel() + gx_host.numel() + gw_host.numel()) * s)},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }

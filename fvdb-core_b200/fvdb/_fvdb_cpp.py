@@ -314,7 +314,10 @@ class _MapCore:
     the built direction and the forward pass of the reversed view.
     """
 
-    def __init__(self, gather, scatter, offsets_host, offsets_dev, nbr, n_feature, n_output, kernel_volume):
+    def __init__(self, gather, scatter, offsets_host, offsets_dev, nbr, n_feature, n_output, kernel_volume, symmetric=False):
+        # symmetric: same grid on both sides, stride 1, odd kernel -> nbr_rev[k] == nbr[K^3 - 1 - k] (row i reaches o through tap k
+        # iff o reaches i through the mirrored tap), so dgrad can run on `nbr` itself with the taps of W mirrored
+        self.symmetric = bool(symmetric)
         self.gather, self.scatter = gather, scatter
         self.offsets_host, self.offsets_dev = offsets_host, offsets_dev
         self.nbr, self._nbr_rev, self._mask_rev = nbr, None, None
@@ -374,6 +377,13 @@ class GatherScatterDefaultTopology:
     def _in_mask(self) -> "torch.Tensor | None":
         return self._core.mask if self._reversed else self._core.mask_rev()
 
+    def _dgrad_plan(self) -> "tuple[torch.Tensor, torch.Tensor | None, bool]":
+        """(input-stationary map, its tile mask, mirror the taps of W?) for dgrad.  A symmetric map serves dgrad as it is --
+        no reversed copy is ever built (half the map memory, a shorter plan build)."""
+        if self._core.symmetric and not self._reversed:
+            return self._core.nbr, self._core.mask, True
+        return self._in_map(), self._in_mask(), False
+
     @property
     def device(self) -> torch.device:
         return self._core.nbr.device
@@ -406,7 +416,8 @@ def _build_topology(feature_grid: GridBatchData, output_grid: GridBatchData, ker
                 _ptr(nbr), pitch, n_out, k3, tap_counts.data_ptr(), offsets_dev.data_ptr(), _ptr(gather), _ptr(scatter), scratch.data_ptr(), scratch_bytes, stream
             )
         )
-    core = _MapCore(gather, scatter, offsets_host, offsets_dev, nbr, n_feat, n_out, k3)
+    symmetric = feature_grid.is_same(output_grid) and st == [1, 1, 1] and all(k % 2 == 1 for k in ks)
+    core = _MapCore(gather, scatter, offsets_host, offsets_dev, nbr, n_feat, n_out, k3, symmetric=symmetric)
     return GatherScatterDefaultTopology(core, ks, st, transposed, reversed_view=False)
 
 
@@ -462,13 +473,13 @@ def _working_dtype(features: torch.Tensor, weights: torch.Tensor) -> torch.dtype
     return working
 
 
-def _pack_weights(weights: torch.Tensor, working: torch.dtype, layout: int) -> torch.Tensor:
+def _pack_weights(weights: torch.Tensor, working: torch.dtype, layout: int, flip_taps: bool = False) -> torch.Tensor:
     cout, cin, k0, k1, k2 = weights.shape
     out = torch.empty((k0 * k1 * k2, cin, cout) if layout == 0 else (k0 * k1 * k2, cout, cin), dtype=working, device=weights.device)
     strides = (C.c_int64 * 5)(*weights.stride())
     check(
         lib.fvc_pack_weights(
-            _ptr(weights), C.byref(strides), _DTYPE_CODE[weights.dtype], cout, cin, k0, k1, k2, layout, 0, _DTYPE_CODE[working], _ptr(out), _stream(weights.device)
+            _ptr(weights), C.byref(strides), _DTYPE_CODE[weights.dtype], cout, cin, k0, k1, k2, layout, int(flip_taps), _DTYPE_CODE[working], _ptr(out), _stream(weights.device)
         )
     )
     return out
@@ -544,11 +555,12 @@ def _backward(grad_output, features, weights, topo, name, want_transposed, on_gr
         if on_grad_weights is not None:
             on_grad_weights(grad_weights)
         # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (:803-804), output-stationary over features
-        wt = _pack_weights(weights, working, layout=1)
         if n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
             grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
         else:
-            grad_features = _run_conv(grad_output, wt, topo._in_map(), n_out, n_feat, cout, cin, k3, None, topo._in_mask())
+            in_map, in_mask, mirror = topo._dgrad_plan()
+            wt = _pack_weights(weights, working, layout=1, flip_taps=mirror)
+            grad_features = _run_conv(grad_output, wt, in_map, n_out, n_feat, cout, cin, k3, None, in_mask)
     return grad_features, grad_weights
 
 

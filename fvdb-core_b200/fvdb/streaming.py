@@ -38,7 +38,7 @@ class HostPipelinedConv:
         # upload dependencies, read off the map itself: chunk c may start once the chunk holding the largest row it
         # gathers has landed (neighbours never leave the grid, but a grid can span any number of chunks)
         self.fwd_needs = self._last_chunk_needed(self.topo._out_map())
-        self.bwd_needs = self._last_chunk_needed(self.topo._in_map())
+        self.bwd_needs = self._last_chunk_needed(self.topo._dgrad_plan()[0])
 
     def _last_chunk_needed(self, nbr: torch.Tensor) -> list[int]:
         tops = torch.stack([nbr[:, r0:r1].amax() for r0, r1 in self.bounds]).tolist()  # one sync, at construction
@@ -93,9 +93,10 @@ class HostPipelinedConv:
         dy = torch.empty((n, cout), dtype=dtype, device=dev)
         y = torch.empty((n, cout), dtype=dtype, device=dev)
         gx = torch.empty((n, cin), dtype=dtype, device=dev)
-        w_fwd, w_bwd = cpp._pack_weights(weights, dtype, 0), cpp._pack_weights(weights, dtype, 1)
+        in_map, in_mask, mirror = topo._dgrad_plan()
+        w_fwd, w_bwd = cpp._pack_weights(weights, dtype, 0), cpp._pack_weights(weights, dtype, 1, flip_taps=mirror)
         gw_acc = torch.zeros(tuple(weights.shape), dtype=torch.float32, device=dev)
-        out_map, out_mask, in_map, in_mask = topo._out_map(), topo._out_mask(), topo._in_map(), topo._in_mask()
+        out_map, out_mask = topo._out_map(), topo._out_mask()
         self.s_in.wait_stream(main)
         self.s_out.wait_stream(main)
         x_ready, dy_ready = [], []

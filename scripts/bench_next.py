@@ -40,7 +40,7 @@ res["conv_grid k=3 s=1 (27 candidates / voxel + build)"] = row(timed(lambda: gri
 res["conv_grid outputs"] = {"k2s2_voxels": down.total_voxels, "k3s1_voxels": dil.total_voxels}
 k = 3
 res["plan 3^3 (map + CSR + tile masks + reversed map, python incl. one sync)"] = row(
-    timed(lambda: fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid)._backend.topology._in_map(), 5), 128 * leaves + 4 * n * 27 * 2 * 3)
+    timed(lambda: fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid)._backend.topology._dgrad_plan(), 5), 128 * leaves + 4 * n * 27 * 2 * 3)
 q = grid.ijk
 res["neighbor_indexes extent=1 (27 lookups / voxel, int64 out)"] = row(timed(lambda: grid.neighbor_indexes(q, 1)), n * (12 + 27 * 8))
 res["ijk_to_index (1 lookup / voxel)"] = row(timed(lambda: grid.ijk_to_index(q)), n * (12 + 8))

@@ -44,7 +44,7 @@ t = timed(lambda: check(lib.fvc_kmap_reverse_dense(gather.data_ptr(), scatter.da
 res["reverse_dense_ms"] = t
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5):
-    plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid); plan._backend.topology._in_map()
+    plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid); plan._backend.topology._dgrad_plan()
 torch.cuda.synchronize(); res["plan_total_ms(python incl. syncs)"] = (time.perf_counter() - t0) / 5 * 1e3
 res["pairs"] = P
 print(json.dumps(res))

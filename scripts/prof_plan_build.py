@@ -10,7 +10,7 @@ grid = fvdb.GridBatch.from_ijk(jt)
 k = cfg["kernel"]
 def build():
     plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid)
-    plan._backend.topology._in_map()
+    plan._backend.topology._dgrad_plan()
     return plan
 for _ in range(3): build()
 torch.cuda.synchronize()
