@@ -388,7 +388,7 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         return src.numel() * src.element_size() * 3 / (p0.elapsed_time(p1) * 1e-3) / 1e9
 
-    link = {"h2d_GBps": round(link_gbps(x, x_host), 1), "d2h_GBps": round(link_gbps(y_host, x), 1)}
+    link = {"h2d_GBps": round(link_gbps(x, x_host), 1), "d2h_GBps": round(link_gbps(gx_host, x), 1)}
 
     stats = torch.tensor([ms, e2e_ms, float(n), float(P)], dtype=torch.float64, device=dev)
     if world > 1:
