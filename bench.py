@@ -44,13 +44,14 @@ CONFIGS = {
     "c4": dict(gen="lidar_sweep", grids=32, voxels=1_000_000, kernel=3, cin=128, cout=128, dtype="bf16", partition="by_grid",
                desc="C4 KITTI-shaped 32 grids x ~1M voxels, 3^3 128->128 bf16, GridBatch partitioned by grid"),
     "c5": dict(gen="random_occupancy", grids=8, voxels=4_979_000, kernel=5, cin=16, cout=16, dtype="bf16", desc="C5 8 grids x ~5M voxels, 5^3 16->16"),
+    "c5f32": dict(gen="random_occupancy", grids=8, voxels=4_979_000, kernel=5, cin=16, cout=16, dtype="f32", desc="C5 8 grids x ~5M voxels, 5^3 16->16 fp32 (three-way bf16 split on the tensor pipe)"),
 }
 DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16, "f64": torch.float64}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same command
-# (profiles/r01_ncu_full_v6_summary.txt); only known for the default workload.
-NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 168.6e6, "dgrad": 297.7e6 + 168.6e6, "wgrad": 595.2e6 + 10.1e6}}
+# (profiles/r01_ncu_full_final_summary.txt); only known for the default workload.
+NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 168.6e6, "dgrad": 297.7e6 + 168.6e6, "wgrad": 595.1e6 + 11.0e6}}
 
 
 def load_peaks() -> dict:
@@ -408,7 +409,7 @@ def run_ours(args, cfg):
                    "sample": f"1 of {cfg['grids']} grids ({vox} voxels, {pairs} pairs) fwd+bwd fp32, median of 2 after 1 warm-up; oracle port of the GatherScatterDefault CPU path"}
         roof = dict(per_kernel[dominant])
         traffic = NCU_TRAFFIC_BYTES.get(args.config, {}).get(dominant) if cfg["grids"] == CONFIGS[args.config]["grids"] else None
-        roof.update({"kernel": dominant, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_ncu_full_v6_summary.txt" if traffic else None,
+        roof.update({"kernel": dominant, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_ncu_full_final_summary.txt" if traffic else None,
                      "peak_source": peaks["source"]})
         line = {
             "metric": "sparse-conv voxels/sec fwd+bwd", "value": total_n / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
