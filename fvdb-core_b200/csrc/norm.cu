@@ -15,6 +15,7 @@ namespace fvc {
 
 constexpr int BN_THREADS = 256;
 constexpr int BN_GRID = 148 * 4;
+constexpr int BN_UNROLL = 4; // rows in flight per thread in the streaming loops
 
 template <typename T> struct RowVec;
 template <> struct RowVec<float> {
@@ -113,14 +114,26 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const T *_
         acc[i] = 0.f;
     if (tid < sp.tpb) {
         const int col = tid % sp.cv;
-        for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += int64_t(gridDim.x) * sp.rpb) {
-            float v[V];
-            RowVec<T>::load(x + row * c + col * V, v);
+        const int64_t step = int64_t(gridDim.x) * sp.rpb;
+        for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += BN_UNROLL * step) {
+            float v[BN_UNROLL][V]; // BN_UNROLL independent 16-byte loads in flight per thread
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                acc[i] += v[i];
-                acc[V + i] = fmaf(v[i], v[i], acc[V + i]);
+            for (int u = 0; u < BN_UNROLL; ++u) {
+                if (row + u * step < n) {
+                    RowVec<T>::load(x + (row + u * step) * c + col * V, v[u]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        v[u][i] = 0.f;
+                }
             }
+#pragma unroll
+            for (int u = 0; u < BN_UNROLL; ++u)
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    acc[i] += v[u][i];
+                    acc[V + i] = fmaf(v[u][i], v[u][i], acc[V + i]);
+                }
         }
     }
     block_column_sum<2 * V>(acc, sp, smem, [&](int col, int i, float total) {
@@ -206,16 +219,25 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const T *__restric
         scale[i] = rsqrtf(var[ch] + eps) * (gamma ? gamma[ch] : 1.f);
         shift[i] = (beta ? beta[ch] : 0.f) - mean[ch] * scale[i];
     }
-    for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += int64_t(gridDim.x) * sp.rpb) {
-        float v[V];
-        RowVec<T>::load(x + row * c + col * V, v);
+    const int64_t step = int64_t(gridDim.x) * sp.rpb;
+    for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += BN_UNROLL * step) {
+        float v[BN_UNROLL][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            v[i] = fmaf(v[i], scale[i], shift[i]);
-            if (relu)
-                v[i] = fmaxf(v[i], 0.f);
+        for (int u = 0; u < BN_UNROLL; ++u)
+            if (row + u * step < n)
+                RowVec<T>::load(x + (row + u * step) * c + col * V, v[u]);
+#pragma unroll
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            if (row + u * step >= n)
+                break;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                v[u][i] = fmaf(v[u][i], scale[i], shift[i]);
+                if (relu)
+                    v[u][i] = fmaxf(v[u][i], 0.f);
+            }
+            RowVec<T>::store(y + (row + u * step) * c + col * V, v[u]);
         }
-        RowVec<T>::store(y + row * c + col * V, v);
     }
 }
 
@@ -241,17 +263,29 @@ bn_backward_reduce_kernel(const T *__restrict__ dy, const T *__restrict__ x, int
             const int ch = col * V + i;
             mu[i] = mean[ch], inv[i] = rsqrtf(var[ch] + eps), g[i] = gamma ? gamma[ch] : 1.f, b[i] = beta ? beta[ch] : 0.f;
         }
-        for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += int64_t(gridDim.x) * sp.rpb) {
-            float xv[V], dv[V];
-            RowVec<T>::load(x + row * c + col * V, xv);
-            RowVec<T>::load(dy + row * c + col * V, dv);
+        const int64_t step = int64_t(gridDim.x) * sp.rpb;
+        for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += 2 * step) {
+            float xv[2][V], dv[2][V]; // two rows (four loads) in flight per thread
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float xhat = (xv[i] - mu[i]) * inv[i];
-                const float dz = (relu && fmaf(xhat, g[i], b[i]) <= 0.f) ? 0.f : dv[i];
-                acc[i] += dz;
-                acc[V + i] = fmaf(dz, xhat, acc[V + i]);
+            for (int u = 0; u < 2; ++u) {
+                if (row + u * step < n) {
+                    RowVec<T>::load(x + (row + u * step) * c + col * V, xv[u]);
+                    RowVec<T>::load(dy + (row + u * step) * c + col * V, dv[u]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        xv[u][i] = mu[i], dv[u][i] = 0.f;
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float xhat = (xv[u][i] - mu[i]) * inv[i];
+                    const float dz = (relu && fmaf(xhat, g[i], b[i]) <= 0.f) ? 0.f : dv[u][i];
+                    acc[i] += dz;
+                    acc[V + i] = fmaf(dz, xhat, acc[V + i]);
+                }
         }
     }
     block_column_sum<2 * V>(acc, sp, smem, [&](int col, int i, float total) {
@@ -305,17 +339,27 @@ bn_backward_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, int6
         m_dz[i] = training ? sums[ch] * inv_count : 0.f;
         m_dzx[i] = training ? sums[c + ch] * inv_count : 0.f;
     }
-    for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += int64_t(gridDim.x) * sp.rpb) {
-        float xv[V], dv[V];
-        RowVec<T>::load(x + row * c + col * V, xv);
-        RowVec<T>::load(dy + row * c + col * V, dv);
+    const int64_t step = int64_t(gridDim.x) * sp.rpb;
+    for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += 2 * step) {
+        float xv[2][V], dv[2][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const float xhat = (xv[i] - mu[i]) * inv[i];
-            const float dz = (relu && fmaf(xhat, g[i], b[i]) <= 0.f) ? 0.f : dv[i];
-            dv[i] = g[i] * inv[i] * (dz - m_dz[i] - xhat * m_dzx[i]);
+        for (int u = 0; u < 2; ++u)
+            if (row + u * step < n) {
+                RowVec<T>::load(x + (row + u * step) * c + col * V, xv[u]);
+                RowVec<T>::load(dy + (row + u * step) * c + col * V, dv[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (row + u * step >= n)
+                break;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float xhat = (xv[u][i] - mu[i]) * inv[i];
+                const float dz = (relu && fmaf(xhat, g[i], b[i]) <= 0.f) ? 0.f : dv[u][i];
+                dv[u][i] = g[i] * inv[i] * (dz - m_dz[i] - xhat * m_dzx[i]);
+            }
+            RowVec<T>::store(dx + (row + u * step) * c + col * V, dv[u]);
         }
-        RowVec<T>::store(dx + row * c + col * V, dv);
     }
 }
 

@@ -1,4 +1,4 @@
-from .modules import AvgPool, BatchNorm, MaxPool, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm, UpsamplingNearest
+from .modules import AvgPool, BatchNorm, GroupNorm, MaxPool, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm, UpsamplingNearest
 from .simple_unet import (
     SimpleUNet,
     SimpleUNetBasicBlock,
@@ -12,7 +12,7 @@ from .simple_unet import (
 )
 
 __all__ = [
-    "AvgPool", "BatchNorm", "MaxPool", "SimpleUNet", "SimpleUNetBasicBlock", "SimpleUNetBottleneck", "SimpleUNetConvBlock", "SimpleUNetDown",
+    "AvgPool", "BatchNorm", "GroupNorm", "MaxPool", "SimpleUNet", "SimpleUNetBasicBlock", "SimpleUNetBottleneck", "SimpleUNetConvBlock", "SimpleUNetDown",
     "SimpleUNetDownUp", "SimpleUNetPad", "SimpleUNetUnpad", "SimpleUNetUp", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm",
     "UpsamplingNearest",
 ]

@@ -118,6 +118,30 @@ class BatchNorm(nn.BatchNorm1d):
             return grid.jagged_like(out) if grid is not None else data.jagged_like(out)
 
 
+class GroupNorm(nn.GroupNorm):
+    """Group normalisation per grid of the batch (mirror of reference fvdb/nn/modules.py:438-480, which loops over the grids
+    and calls torch's GroupNorm on each ``[1, C, N_b]`` slab).  Same statistics -- per (grid, group) over that grid's voxels
+    and the group's channels -- computed for the whole batch at once with segment sums over ``jidx`` (torch ops, autograd)."""
+
+    def forward(self, data: JaggedTensor, grid: GridBatch) -> JaggedTensor:  # type: ignore[override]
+        with record_function(repr(self)):
+            x = data.jdata
+            n, c = x.shape
+            assert c == self.num_channels, "Input feature should have the same number of channels as GroupNorm"
+            groups, per = self.num_groups, c // self.num_groups
+            batches = grid.grid_count
+            owner = grid.jidx.long() if batches > 1 else torch.zeros(n, dtype=torch.long, device=x.device)
+            xg = x.float().reshape(n, groups, per)
+            count = torch.zeros(batches, device=x.device).index_add_(0, owner, torch.ones(n, device=x.device)).clamp_min(1.0) * per
+            mean = torch.zeros((batches, groups), device=x.device).index_add_(0, owner, xg.sum(-1)) / count[:, None]
+            centred = xg - mean[owner][:, :, None]
+            var = torch.zeros((batches, groups), device=x.device).index_add_(0, owner, centred.square().sum(-1)) / count[:, None]
+            out = (centred * torch.rsqrt(var + self.eps)[owner][:, :, None]).reshape(n, c)
+            if self.affine:
+                out = out * self.weight.float() + self.bias.float()
+            return grid.jagged_like(out.to(x.dtype))
+
+
 class SyncBatchNorm(BatchNorm):
     """BatchNorm with statistics over every process of ``process_group`` (mirror of reference modules.py:524-580): the
     per-rank (count, mean, M2) are all-gathered and merged, the two backward sums all-reduced (2*C floats each)."""
