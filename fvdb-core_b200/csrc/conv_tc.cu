@@ -61,7 +61,9 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static constexpr int B_BYTES = NS * CHUNK_BYTES;         // one weight stage: the chunk(s) of one (tap group, channel block)
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * COUT;  // TMEM columns per tile (SPLIT: main | small-term accumulator)
     static constexpr int TMEM_COLS = tmem_cols_for(TILES * ACC_COLS);
-    static constexpr int MAX_UNITS = (SPLIT || TMA) ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS;
+    // unit-list capacity: packed taps (Cin < 64) never exceed 128 groups x 8 tiles; the 2-tile and fp32 shapes trade list
+    // space for a third co-resident CTA / weight chunks
+    static constexpr int MAX_UNITS = (SPLIT || TMA || TILES <= 2 || CIN < 64) ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS;
     static constexpr int THREADS = (PW + 3) * 32;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * BST + 1 + 2 * TC_IDX_RING;
     // one ring entry: 128 map entries per tap of the group; with several taps per entry each tap's 512 bytes are followed
@@ -72,9 +74,11 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(TMA ? 0 : TC_IDX_RING) * RING_BYTES +
                                    size_t(MAX_UNITS) * 2 + 8 * NUM_BARS + 16;
     static_assert(!TMA || CIN >= 64, "the TMA gather path needs one tap per 128-byte row");
-    // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (228 KB per SM, 1 KB reserved per CTA)
+    // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (228 KB per SM, 1 KB reserved per CTA).
+    // Three small CTAs per SM beat two larger ones by ~10 % on the 32- and 64-channel shapes: more independent
+    // producer -> MMA -> commit chains hide the per-unit hand-off latency (profiles/r01_experiments.md)
     static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = int(233472 / (SMEM + 1024 + 768));
-    static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > 2 ? 2 : BY_TMEM) : (BY_SMEM > 2 ? 2 : BY_SMEM);
+    static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > 3 ? 3 : BY_TMEM) : (BY_SMEM > 3 ? 3 : BY_SMEM);
     static_assert(CTAS_PER_SM >= 1, "configuration does not fit one SM");
     static_assert((CIN % 64 == 0 || CIN == 32 || CIN == 16) && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * ACC_COLS <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
@@ -696,35 +700,14 @@ int tc_forward(const ConvArgs &a) {
     tc_pack_b_kernel<<<int(ceil_div(chunks16, 256) > 1184 ? 1184 : ceil_div(chunks16, 256)), 256, 0, a.stream>>>(
         reinterpret_cast<const uint16_t *>(a.w), a.k3, a.cin, a.cout, reinterpret_cast<uint4 *>(img));
     FVC_LAUNCH_CHECK();
-    // experiment knob (scripts/bench_variants.py): alternative pipeline shapes
-    const char *variant_env = getenv("FVC_TC_VARIANT");
-    const int variant = variant_env ? atoi(variant_env) : 0;
+    // experiment knob (scripts/bench_variants.py, profiles/r01_experiments.md): alternative pipeline shapes of the 64 -> 64 kernel
     if (a.cin == 64 && a.cout == 64) {
-        switch (variant) {
-        case 1: return launch_tc_fwd<64, 64, 4, 4, 3, 8>(a, a.x, img);
-        case 2: return launch_tc_fwd<64, 64, 8, 8, 4, 4>(a, a.x, img);
-        case 3: return launch_tc_fwd<64, 64, 4, 3, 3, 4>(a, a.x, img);
-        case 4: return launch_tc_fwd<64, 64, 2, 4, 3, 4>(a, a.x, img);
+        const char *variant_env = getenv("FVC_TC_VARIANT");
+        switch (variant_env ? atoi(variant_env) : 0) {
+        case 1: return launch_tc_fwd<64, 64, 4, 4, 3, 4>(a, a.x, img);               // two 4-tile CTAs per SM (the round-1 default until v7)
+        case 2: return launch_tc_fwd<64, 64, 8, 8, 4, 4>(a, a.x, img);               // one 8-tile CTA per SM
+        case 3: return launch_tc_fwd<64, 64, 4, 4, 3, 8>(a, a.x, img);               // 8 producer warps
         case 10: return launch_tc_fwd<64, 64, 4, 4, 3, 4, false, true>(a, a.x, img); // TMA gather4 producer
-        case 11: return launch_tc_fwd<64, 64, 4, 5, 3, 4, false, true>(a, a.x, img);
-        case 12: return launch_tc_fwd<64, 64, 4, 3, 3, 4, false, true>(a, a.x, img);
-        default: break;
-        }
-    }
-    if (a.cin == 128 && a.cout == 128) {
-        switch (variant) {
-        case 1: return launch_tc_fwd<128, 128, 2, 3, 2, 4>(a, a.x, img);
-        case 2: return launch_tc_fwd<128, 128, 4, 6, 4, 4>(a, a.x, img);
-        case 3: return launch_tc_fwd<128, 128, 4, 8, 3, 8>(a, a.x, img);
-        case 4: return launch_tc_fwd<128, 128, 2, 4, 2, 4>(a, a.x, img);
-        default: break;
-        }
-    }
-    if (a.cin == 16 && a.cout == 16) {
-        switch (variant) {
-        case 1: return launch_tc_fwd<16, 16, 8, 5, 3, 4>(a, a.x, img);
-        case 2: return launch_tc_fwd<16, 16, 8, 4, 3, 8>(a, a.x, img);
-        case 3: return launch_tc_fwd<16, 16, 4, 5, 3, 4>(a, a.x, img);
         default: break;
         }
     }
@@ -733,8 +716,8 @@ int tc_forward(const ConvArgs &a) {
         return launch_tc_fwd<CI, CO, T, S, B, 4>(a, a.x, img);
 #define FVC_TC_CIN(CI)           \
     FVC_TC_CASE(CI, 16, 8, 4, 3)  \
-    FVC_TC_CASE(CI, 32, 8, 4, 3)  \
-    FVC_TC_CASE(CI, 64, 4, 4, 3)  \
+    FVC_TC_CASE(CI, 32, 4, 3, 2)  \
+    FVC_TC_CASE(CI, 64, 2, 3, 2)  \
     FVC_TC_CASE(CI, 128, 2, 3, 2) \
     FVC_TC_CASE(CI, 256, 2, 6, 3)
     FVC_TC_CIN(16)

@@ -15,7 +15,7 @@ namespace fvc {
 
 constexpr int BN_THREADS = 256;
 constexpr int BN_GRID = 148 * 4;
-constexpr int BN_UNROLL = 4; // rows in flight per thread in the streaming loops
+constexpr int BN_UNROLL = 1; // rows in flight per thread in the forward loops (4 measured slower on bf16: registers, not loads, limit)
 
 template <typename T> struct RowVec;
 template <> struct RowVec<float> {

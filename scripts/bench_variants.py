@@ -17,7 +17,7 @@ w = (torch.randn((cout, cin, cfg["kernel"], cfg["kernel"], cfg["kernel"]), devic
 wp = cpp._pack_weights(w, dtype, 0)
 ref = None
 debugs = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
-for variant, debug in [(int(v), d) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,1,2,3,4,5,6".split(",")) for d in debugs]:
+for variant, debug in [(int(v), d) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,1,2,3,10".split(",")) for d in debugs]:
     os.environ["FVC_TC_VARIANT"] = str(variant)
     os.environ["FVC_TC_DEBUG"] = str(debug)
     f = lambda: cpp._run_conv(x, wp, topo._out_map(), n, n, cin, cout, k3, None, topo._out_mask())
