@@ -1,12 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-for lib in fvdb-core_b200/fvdb/libfvdbconv.so fvdb-core_b200/fvdb/libfvdbconv_bn1.so fvdb-core_b200/fvdb/libfvdbconv.so fvdb-core_b200/fvdb/libfvdbconv_bn1.so; do
-FVC_LIB=$PWD/$lib timeout 300 python scripts/bench_next.py c2 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('$lib', {k.split('(')[0][15:]:v['ms'] for k,v in d.items() if k.startswith('BatchNorm+ReLU')})"
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | grep -E "^E  |passed|failed|Error" | head -20 | tee gpurun_out/pytest_gpu.log
+for c in c2 c3; do
+timeout 300 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$c', d['ms_per_step'], {k:(round(v['ms'],4), round(v['frac'],3)) for k,v in (d.get('roofline_kernels') or {}).items()}, (d.get('roofline_step') or {}).get('frac'))"
 done
-timeout 300 python scripts/bench_variants.py c2x128 0,5,6 2>&1 | tail -3
-timeout 300 python scripts/bench_variants.py c1 0,5,6 2>&1 | tail -3
-timeout 300 python scripts/bench_variants.py c3 0,5,6 2>&1 | tail -3
