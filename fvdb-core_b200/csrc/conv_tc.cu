@@ -715,7 +715,7 @@ int tc_forward(const ConvArgs &a) {
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_fwd<CI, CO, T, S, B, 4>(a, a.x, img);
 #define FVC_TC_CIN(CI)           \
-    FVC_TC_CASE(CI, 16, 8, 4, 3)  \
+    FVC_TC_CASE(CI, 16, 8, 3, 2)  \
     FVC_TC_CASE(CI, 32, 4, 3, 2)  \
     FVC_TC_CASE(CI, 64, 2, 3, 2)  \
     FVC_TC_CASE(CI, 128, 2, 3, 2) \
