@@ -33,7 +33,9 @@ constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 reduction-side el
 
 // Small channel counts are packed like in the forward kernel: an A block holds G = 64 / CIN taps x CIN channels;
 // a dY row narrower than 64 channels is zero-padded to one 128-byte row (N = 64 for the MMA, extra columns unused).
-template <int CIN, int COUT, int STAGES, bool SPLIT = false> struct TcWgradCfg {
+// CTAS: co-resident CTAs per SM (TMEM columns are split between them).  Two half-size CTAs hide each other's per-unit
+// hand-off latency on the narrow-output shapes, where a dY tile is cheap to load twice.
+template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1> struct TcWgradCfg {
     static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per A block
     static constexpr int CB = CIN >= 64 ? CIN / 64 : 1;     // A channel blocks per tap (group)
     static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a row
@@ -43,8 +45,9 @@ template <int CIN, int COUT, int STAGES, bool SPLIT = false> struct TcWgradCfg {
     static constexpr int NS = SPLIT ? 3 : 1;                // bf16 splits per fp32 operand
     static constexpr int XS = NS * CIN, YS = NS * COUT;     // row strides (elements) of the (split) feature / grad rows
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * NPAD; // TMEM columns per unit (SPLIT: main | small-term accumulator)
-    static constexpr int MAX_UNITS = 512 / ACC_COLS;        // accumulators that fit TMEM
-    static constexpr int BSTAGES = (SPLIT && COUT >= 128) ? 1 : 2;
+    static constexpr int TMEM_COLS = 512 / CTAS;            // this CTA's share of the SM's tensor memory
+    static constexpr int MAX_UNITS = TMEM_COLS / ACC_COLS;  // accumulators that fit
+    static constexpr int BSTAGES = ((SPLIT && COUT >= 128) || CTAS > 1) ? 1 : 2;
     static constexpr int RING = G == 4 ? 4 : 8;             // kernel-map ring depth
     static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;    // 128 int32 per tap (+ a 16-byte pad so packed taps sit on different banks)
     static constexpr int RING_BYTES = 2 * G * SUB_STRIDE;   // two blocks x G taps
@@ -55,7 +58,8 @@ template <int CIN, int COUT, int STAGES, bool SPLIT = false> struct TcWgradCfg {
     static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128 || CIN == 256, "unsupported Cin");
     static_assert(COUT == 16 || COUT == 32 || COUT == 64 || COUT == 128 || COUT == 256, "unsupported Cout");
     static_assert(!SPLIT || COUT <= 128, "fp32 split: Cout <= 128");
-    static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+    static_assert((SMEM + 1024 + 768) * CTAS <= 233472, "shared memory budget exceeded");
+    static_assert(CTAS == 1 || CTAS == 2, "one or two CTAs per SM");
 };
 
 // One warp's share (rows [32w, 32w+32)) of a 128-row x 128-byte swizzled block: 8 lanes q cover one row (one full
@@ -74,12 +78,12 @@ __device__ __forceinline__ void lds_v4x2(uint32_t addr, int (&v)[8]) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr + 16) : "memory");
 }
 
-template <int CIN, int COUT, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+template <int CIN, int COUT, int STAGES, bool SPLIT, int CTAS>
+__global__ void __launch_bounds__(WG_THREADS, CTAS)
 conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
                      int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
                      int tiles_per_chunk, int seg_tiles, uint32_t idesc, float *__restrict__ partial) {
-    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT>;
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS>;
     constexpr int G = Cfg::G, CB = Cfg::CB, CPT = Cfg::CPT, NB = Cfg::NB, NPAD = Cfg::NPAD, RING = Cfg::RING;
     constexpr int NS = Cfg::NS, XS = Cfg::XS, YS = Cfg::YS, ACC = Cfg::ACC_COLS, BSTAGES = Cfg::BSTAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -156,7 +160,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         fence_mbar_init();
     }
     if (warp == WG_WARP_MMA)
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -376,7 +380,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     tc_fence_before();
     __syncthreads();
     if (warp == WG_WARP_MMA)
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -386,15 +390,19 @@ struct WgradPlan {
 
 constexpr int WG_SPLIT_SEG_TILES = 32; // fp32: drain the accumulators every 32 row tiles (<= 256 full-magnitude MMA steps)
 
+// narrow outputs (Cout <= 32, bf16 / f16) run two half-TMEM CTAs per SM
+static inline int wgrad_ctas(int cout, bool split) { return (!split && cout <= 32) ? 2 : 1; }
+
 static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split) {
     WgradPlan p;
+    const int ctas = wgrad_ctas(cout, split);
     const int total_blocks = cin >= 64 ? k3 * (cin / 64) : int(ceil_div(k3, 64 / cin));
     const int total_units = (total_blocks + 1) / 2;
-    const int max_units = 512 / ((split ? 2 : 1) * (cout >= 64 ? cout : 64));
+    const int max_units = (512 / ctas) / ((split ? 2 : 1) * (cout >= 64 ? cout : 64));
     p.groups = int(ceil_div(total_units, max_units));
     p.units_per_group = int(ceil_div(total_units, p.groups)); // balanced groups
     const int64_t tiles = ceil_div(n_out, WG_TILE);
-    int64_t chunks = 148 / p.groups; // one CTA per SM (TMEM: 512 columns each)
+    int64_t chunks = 148 * ctas / p.groups; // one wave of resident CTAs (TMEM: 512 columns per SM)
     if (chunks < 1)
         chunks = 1;
     if (chunks > tiles)
@@ -408,10 +416,11 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split
 // tc_split_rows_kernel lives in conv_tc.cu
 int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t stream);
 
-template <int CIN, int COUT, int STAGES, bool SPLIT = false>
+template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1>
 static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, float *partial) {
-    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT>;
-    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT>;
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS>;
+    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT, CTAS>;
+    FVC_REQUIRE(CTAS == wgrad_ctas(COUT, SPLIT), FVC_ERR_RUNTIME, "weight-gradient plan / kernel shape mismatch");
     static bool configured = false;
     if (!configured) {
         FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
@@ -492,9 +501,12 @@ int tc_wgrad(const WgradArgs &a) {
 #define FVC_WG_CASE(CI, CO, S)       \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S>(a, a.x, a.dy, partial);
+#define FVC_WG_CASE2(CI, CO, S)      \
+    if (a.cin == CI && a.cout == CO) \
+        return launch_tc_wgrad<CI, CO, S, false, 2>(a, a.x, a.dy, partial);
 #define FVC_WG_CIN(CI)       \
-    FVC_WG_CASE(CI, 16, 4)   \
-    FVC_WG_CASE(CI, 32, 4)   \
+    FVC_WG_CASE2(CI, 16, 2)  \
+    FVC_WG_CASE2(CI, 32, 2)  \
     FVC_WG_CASE(CI, 64, 4)   \
     FVC_WG_CASE(CI, 128, 4)  \
     FVC_WG_CASE(CI, 256, 2)
@@ -505,6 +517,7 @@ int tc_wgrad(const WgradArgs &a) {
     FVC_WG_CIN(256)
 #undef FVC_WG_CIN
 #undef FVC_WG_CASE
+#undef FVC_WG_CASE2
     return set_error(FVC_ERR_UNSUPPORTED, "no tensor-core wgrad kernel for channels %d -> %d", a.cin, a.cout);
 }
 
