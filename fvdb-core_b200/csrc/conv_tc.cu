@@ -718,7 +718,7 @@ int tc_forward(const ConvArgs &a) {
     FVC_TC_CASE(CI, 16, 8, 3, 2)  \
     FVC_TC_CASE(CI, 32, 4, 3, 2)  \
     FVC_TC_CASE(CI, 64, 2, 3, 2)  \
-    FVC_TC_CASE(CI, 128, 2, 3, 2) \
+    FVC_TC_CASE(CI, 128, 1, 2, 2) \
     FVC_TC_CASE(CI, 256, 2, 6, 3)
     FVC_TC_CIN(16)
     FVC_TC_CIN(32)
