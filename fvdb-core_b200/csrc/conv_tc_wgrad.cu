@@ -390,8 +390,8 @@ struct WgradPlan {
 
 constexpr int WG_SPLIT_SEG_TILES = 32; // fp32: drain the accumulators every 32 row tiles (<= 256 full-magnitude MMA steps)
 
-// narrow outputs (Cout <= 32, bf16 / f16) run two half-TMEM CTAs per SM
-static inline int wgrad_ctas(int cout, bool split) { return (!split && cout <= 32) ? 2 : 1; }
+// outputs up to 64 channels (bf16 / f16; 64 TMEM columns per accumulator) run two half-TMEM CTAs per SM
+static inline int wgrad_ctas(int cout, bool split) { return (!split && cout <= 64) ? 2 : 1; }
 
 static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split) {
     WgradPlan p;
@@ -507,7 +507,7 @@ int tc_wgrad(const WgradArgs &a) {
 #define FVC_WG_CIN(CI)       \
     FVC_WG_CASE2(CI, 16, 2)  \
     FVC_WG_CASE2(CI, 32, 2)  \
-    FVC_WG_CASE(CI, 64, 4)   \
+    FVC_WG_CASE2(CI, 64, 2)  \
     FVC_WG_CASE(CI, 128, 4)  \
     FVC_WG_CASE(CI, 256, 2)
     FVC_WG_CIN(16)
