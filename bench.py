@@ -51,7 +51,7 @@ DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16, "f
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same command
 # (profiles/r01_ncu_full_final_summary.txt); only known for the default workload.
-NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 171.0e6, "dgrad": 297.7e6 + 171.0e6, "wgrad": 593.5e6 + 13.5e6}}
+NCU_TRAFFIC_BYTES = {"c2": {"fwd": 297.7e6 + 170.9e6, "dgrad": 297.7e6 + 170.9e6, "wgrad": 947.3e6 + 15.0e6}}
 
 
 def load_peaks() -> dict:
