@@ -194,3 +194,38 @@ def test_group_norm_matches_per_grid_torch_group_norm():
     (g,) = torch.autograd.grad(out.square().sum(), x)
     (gw,) = torch.autograd.grad(want.square().sum(), x)
     torch.testing.assert_close(g, gw, rtol=1e-4, atol=1e-5)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    # `bench.py --impl reference` needs no GPU (it times the oracle port on the host cores); guard its JSON contract here.
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--config", "c1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()[-1]
+    line = json.loads(out)
+    assert line["impl"] == "reference" and line["metric"] == "sparse-conv voxels/sec fwd+bwd" and line["unit"] == "voxels/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "sample" in line["config"]
+
+
+def test_bench_partition_by_grid_is_a_disjoint_cover():
+    # C4-style strong scaling: every rank derives the same LPT partition of the one batch and keeps its own grids.
+    sys_path_bench = str(REPO)
+    import sys
+
+    if sys_path_bench not in sys.path:
+        sys.path.insert(0, sys_path_bench)
+    import bench
+
+    cfg = dict(gen="sphere_shell", grids=5, voxels=1500, kernel=3, cin=16, cout=16, dtype="bf16", partition="by_grid", desc="test")
+    whole = bench.make_coords({**cfg, "partition": None}, 0, "cpu", 1)
+    parts = [bench.make_coords(cfg, rank, "cpu", 2) for rank in range(2)]
+    assert sum(len(p) for p in parts) == 5 and all(len(p) >= 2 for p in parts)
+    seen = sorted(int(c.shape[0]) for p in parts for c in p)
+    assert seen == sorted(int(c.shape[0]) for c in whole)
+    loads = [sum(int(c.shape[0]) for c in p) for p in parts]
+    assert abs(loads[0] - loads[1]) <= max(int(c.shape[0]) for c in whole)  # LPT: imbalance bounded by one grid
