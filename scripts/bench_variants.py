@@ -16,10 +16,8 @@ x = torch.randn((n, cin), device=dev).to(dtype)
 w = (torch.randn((cout, cin, cfg["kernel"], cfg["kernel"], cfg["kernel"]), device=dev) * 0.02).to(dtype)
 wp = cpp._pack_weights(w, dtype, 0)
 ref = None
-debugs = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
-for variant, debug in [(int(v), d) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,1,2,3,10".split(",")) for d in debugs]:
+for variant in [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,1,2,3,10".split(","))]:
     os.environ["FVC_TC_VARIANT"] = str(variant)
-    os.environ["FVC_TC_DEBUG"] = str(debug)
     f = lambda: cpp._run_conv(x, wp, topo._out_map(), n, n, cin, cout, k3, None, topo._out_mask())
     y = f(); torch.cuda.synchronize()
     if ref is None: ref = y
@@ -27,4 +25,4 @@ for variant, debug in [(int(v), d) for v in (sys.argv[2].split(",") if len(sys.a
     a.record()
     for _ in range(5): f()
     b.record(); torch.cuda.synchronize()
-    print(json.dumps({"variant": variant, "debug": debug, "fwd_ms": a.elapsed_time(b) / 5, "max_abs_diff_vs_v0": float((y.float() - ref.float()).abs().max())}), flush=True)
+    print(json.dumps({"variant": variant, "fwd_ms": a.elapsed_time(b) / 5, "max_abs_diff_vs_v0": float((y.float() - ref.float()).abs().max())}), flush=True)
