@@ -360,7 +360,7 @@ def run_ours(args, cfg):
     if cpp.lib.fvc_conv_scratch_bytes(n, n, cin, cout, k3, code) > 0 and dtype != torch.float32 and has_fixed_topology(plan):  # tensor-core path available
         from fvdb.streaming import HostPipelinedConv
 
-        pipe = HostPipelinedConv(plan, num_chunks=8)
+        pipe = HostPipelinedConv(plan, num_chunks=args.e2e_chunks)
         e2e_mode = f"3-stream overlap, {len(pipe.bounds)} row chunks (fvdb.streaming.HostPipelinedConv)"
 
         def e2e_step():  # noqa: F811
@@ -622,6 +622,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="row chunks of the host-buffer pipeline (upload / convolve / read back overlap)")
     ap.add_argument("--graph", action="store_true", help="c3 (1 GPU): capture the training step in one CUDA graph and replay it")
     ap.add_argument("--profile", action="store_true", help="c3: print a torch.profiler kernel-time summary of one step to stderr")
     ap.add_argument("--torch-bn", action="store_true", help="c3: torch BatchNorm1d + separate ReLU (the reference's composition) instead of the fused kernels")
