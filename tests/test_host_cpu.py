@@ -229,3 +229,14 @@ def test_bench_partition_by_grid_is_a_disjoint_cover():
     assert seen == sorted(int(c.shape[0]) for c in whole)
     loads = [sum(int(c.shape[0]) for c in p) for p in parts]
     assert abs(loads[0] - loads[1]) <= max(int(c.shape[0]) for c in whole)  # LPT: imbalance bounded by one grid
+
+
+def test_header_is_plain_c():
+    # The drop-in boundary is a C ABI: include/fvdbconv.h must compile as C11 (no torch / C++ types in the signatures).
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", str(REPO / "include" / "fvdbconv.h")], check=True)
