@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- sparse-conv voxels/sec forward+backward over a GridBatch (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c2f32|c2x128|c3|c4|c5|c5f32]
 
 One "step" = one pass of the hot path over one batch: forward + dgrad + wgrad of a 3^3 64->64 bf16
 SparseConv3d-shaped plan (BASELINE.json configs[1]: 8 indoor grids x ~200 k voxels, same-topology target),
 kernel map prebuilt ("topology amortized", as the reference's own benches do).  For N > 1 (launched under
-torch.distributed.run) every rank owns whole grids (its own batch of 8: weak scaling) and the step ends
-with the NCCL all-reduce of grad_weights, the path's only exchange.
+torch.distributed.run) every rank owns whole grids (its own batch of 8: weak scaling; --config c4 partitions ONE 32-grid
+batch by grid: strong scaling) and the step contains the NCCL all-reduce of grad_weights, the path's only exchange, issued
+asynchronously behind wgrad so that it overlaps dgrad.  --config c3 runs the sparse UNet block-stack training step.
 
 Prints ONE JSON line on rank 0; see the task contract for the keys.  `value` is timed with inputs
 resident in HBM; `e2e` goes through the same C-ABI-backed calls with HOST (pinned) buffers, H2D and D2H
