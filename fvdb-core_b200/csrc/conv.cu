@@ -16,16 +16,10 @@ static int check_common(const void *x, const void *w, int64_t n_in, int64_t n_ou
     return FVC_OK;
 }
 
-extern "C" {
-
-size_t fvc_conv_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype) {
-    return tc_forward_supported(cin, cout, kernel_volume, dtype) ? tc_forward_scratch_bytes(n_in, n_out, cin, cout, kernel_volume, dtype) : 0;
-}
-
-int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
-                     const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
-                     int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream) {
-    int rc = check_common(x, w_packed, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_forward");
+static int run_forward(const void *x, const void *w, bool w_prepared, bool x_split, const Epilogue &epi, void *y, const int32_t *nbr, int64_t pitch,
+                       const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                       int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream) {
+    int rc = check_common(x, w, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_forward");
     if (rc)
         return rc;
     FVC_REQUIRE(path >= 0 && path <= 2, FVC_ERR_VALUE, "path must be 0 (auto), 1 (CUDA-core) or 2 (tensor-core)");
@@ -34,27 +28,115 @@ int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void
     FVC_REQUIRE(y && (kernel_volume == 0 || nbr), FVC_ERR_RUNTIME, "fvc_conv_forward: null output / map pointer");
     FVC_REQUIRE(pitch >= n_out, FVC_ERR_RUNTIME, "fvc_conv_forward: map pitch %lld < output rows %lld", (long long)pitch,
                 (long long)n_out);
-    ConvArgs a{x, w_packed, bias, y, nbr, pitch, tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype, scratch, scratch_bytes,
-               reinterpret_cast<cudaStream_t>(stream)};
+    ConvArgs a{x, w, epi, y, nbr, pitch, tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype, scratch, scratch_bytes,
+               reinterpret_cast<cudaStream_t>(stream), w_prepared, x_split};
     const bool tc_ok = tc_forward_supported(cin, cout, kernel_volume, dtype);
     if (path == 2 && !tc_ok)
         return set_error(FVC_ERR_UNSUPPORTED, "tensor-core path does not admit dtype code %d with channels %d -> %d", dtype, cin, cout);
     if (tc_ok && path != 1)
         return tc_forward(a);
+    FVC_REQUIRE(!x_split, FVC_ERR_UNSUPPORTED, "fvc_conv_forward: split feature rows are a tensor-core (fp32) operand");
+    FVC_REQUIRE(!epi.scale && !epi.shift && !epi.residual && !epi.relu && !epi.stats, FVC_ERR_UNSUPPORTED,
+                "fvc_conv_forward_ex: the fused block epilogue runs on the tensor-core path only (dtype code %d, channels %d -> %d)", dtype, cin, cout);
     return simt_forward(a);
 }
 
-size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout, int64_t kernel_volume,
-                                    int32_t dtype) {
-    size_t simt = simt_wgrad_scratch_bytes(total_pairs, cin, cout, kernel_volume, dtype);
-    size_t tc = tc_wgrad_supported(cin, cout, kernel_volume, dtype) ? tc_wgrad_scratch_bytes(n_in, n_out, cin, cout, kernel_volume, dtype) : 0;
-    return simt > tc ? simt : tc;
+extern "C" {
+
+int fvc_set_tuning(int32_t key, int32_t value) {
+    FVC_REQUIRE(key == 0, FVC_ERR_VALUE, "unknown tuning key %d", key);
+    g_tc_variant = value;
+    return FVC_OK;
+}
+
+size_t fvc_conv_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype) {
+    return tc_forward_supported(cin, cout, kernel_volume, dtype) ? tc_forward_scratch_bytes(n_in, n_out, cin, cout, kernel_volume, dtype) : 0;
+}
+
+int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
+                     const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                     int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream) {
+    Epilogue epi;
+    epi.bias = bias;
+    return run_forward(x, w_packed, false, false, epi, y, nbr, pitch, tile_mask, n_in, n_out, cin, cout, kernel_volume, dtype, path, scratch,
+                       scratch_bytes, stream);
+}
+
+static inline bool takes_tc(int32_t cin, int32_t cout, int64_t k3, int32_t dtype, int32_t path) {
+    return path != 1 && tc_forward_supported(cin, cout, k3, dtype);
+}
+
+size_t fvc_conv_weights_bytes(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path) {
+    if (takes_tc(cin, cout, kernel_volume, dtype, path))
+        return tc_weight_image_bytes(cin, cout, kernel_volume, dtype);
+    return align_up(size_t(kernel_volume) * size_t(cin) * size_t(cout) * dtype_size(dtype), 256);
+}
+
+int fvc_conv_prepare_weights(const void *weights, const int64_t strides[5], int32_t dtype_in, int32_t cout, int32_t cin, int32_t k0, int32_t k1,
+                             int32_t k2, int32_t transpose, int32_t flip_taps, int32_t dtype, int32_t path, void *prepared, size_t prepared_bytes,
+                             fvc_stream_t stream) {
+    FVC_REQUIRE(dtype_size(dtype_in) && dtype_size(dtype), FVC_ERR_UNSUPPORTED, "unsupported weight dtype");
+    FVC_REQUIRE(cin > 0 && cout > 0 && k0 > 0 && k1 > 0 && k2 > 0, FVC_ERR_RUNTIME, "fvc_conv_prepare_weights: empty weight tensor");
+    const int64_t k3 = int64_t(k0) * k1 * k2;
+    const int32_t cin_e = transpose ? cout : cin, cout_e = transpose ? cin : cout; // the executor's reduction / output channels
+    FVC_REQUIRE(prepared && prepared_bytes >= fvc_conv_weights_bytes(cin_e, cout_e, k3, dtype, path), FVC_ERR_RUNTIME,
+                "fvc_conv_prepare_weights: output buffer too small");
+    FVC_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 255) == 0, FVC_ERR_RUNTIME, "fvc_conv_prepare_weights: output must be 256-byte aligned");
+    if (takes_tc(cin_e, cout_e, k3, dtype, path))
+        return tc_prepare_weights(weights, strides, dtype_in, cout, cin, k0, k1, k2, transpose, flip_taps, dtype, prepared,
+                                  reinterpret_cast<cudaStream_t>(stream));
+    return fvc_pack_weights(weights, strides, dtype_in, cout, cin, k0, k1, k2, transpose ? 1 : 0, flip_taps, dtype, prepared, stream);
+}
+
+int64_t fvc_conv_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, int32_t *rows_per_block) {
+    if (!takes_tc(cin, cout, kernel_volume, dtype, path)) {
+        if (rows_per_block)
+            *rows_per_block = 0;
+        return 0; // the fused statistics exist on the tensor-core path only
+    }
+    return tc_stats_blocks(n_out, cin, cout, dtype, rows_per_block);
+}
+
+int fvc_conv_forward_ex(const void *x, int32_t x_is_split, const void *w_prepared, const FvcConvEpilogue *epilogue, void *y, const int32_t *nbr,
+                        int64_t pitch, const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume,
+                        int32_t dtype, int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream) {
+    Epilogue epi;
+    if (epilogue) {
+        epi.bias = epilogue->bias, epi.scale = epilogue->scale, epi.shift = epilogue->shift, epi.residual = epilogue->residual;
+        epi.relu = epilogue->relu, epi.stats = epilogue->stats;
+    }
+    return run_forward(x, w_prepared, true, x_is_split != 0, epi, y, nbr, pitch, tile_mask, n_in, n_out, cin, cout, kernel_volume, dtype, path, scratch,
+                       scratch_bytes, stream);
+}
+
+int fvc_split_rows(const float *x, int64_t n, int32_t channels, void *split_rows, fvc_stream_t stream) {
+    FVC_REQUIRE(channels > 0 && channels % 8 == 0, FVC_ERR_UNSUPPORTED, "fvc_split_rows: channel count %d must be a multiple of 8", channels);
+    FVC_REQUIRE(n == 0 || (x && split_rows), FVC_ERR_RUNTIME, "fvc_split_rows: null pointer");
+    FVC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(split_rows) & 15) == 0, FVC_ERR_RUNTIME,
+                "fvc_split_rows: pointers must be 16-byte aligned");
+    return tc_split_rows(x, n, channels, reinterpret_cast<uint16_t *>(split_rows), reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t max_pairs_per_tap, int32_t cin, int32_t cout, int64_t kernel_volume,
+                                    int32_t dtype, int32_t path, int32_t has_dense_map) {
+    // sized for the kernel family that will run (fvc_conv_wgrad makes the same choice)
+    if (path != 1 && has_dense_map && tc_wgrad_supported(cin, cout, kernel_volume, dtype))
+        return tc_wgrad_scratch_bytes(n_in, n_out, cin, cout, kernel_volume, dtype);
+    return simt_wgrad_scratch_bytes(max_pairs_per_tap, cin, cout, kernel_volume, dtype);
 }
 
 int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const int32_t *scatter,
                    const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
                    const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                    int32_t path, void *grad_w, void *scratch, size_t scratch_bytes, fvc_stream_t stream_) {
+    return fvc_conv_wgrad_ex(x, 0, dy, 0, gather, scatter, offsets_host, offsets_dev, nbr, pitch, tile_mask, n_in, n_out, cin, cout, kernel_volume, dtype,
+                             path, grad_w, scratch, scratch_bytes, stream_);
+}
+
+int fvc_conv_wgrad_ex(const void *x, int32_t x_is_split, const void *dy, int32_t dy_is_split, const int32_t *gather, const int32_t *scatter,
+                      const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
+                      const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
+                      int32_t path, void *grad_w, void *scratch, size_t scratch_bytes, fvc_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     // (dy stands in for the weights argument of the shared check; it may be NULL only when there are no output rows)
     int rc = check_common(x, n_out == 0 ? reinterpret_cast<const void *>(1) : dy, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_wgrad");
@@ -72,12 +154,13 @@ int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const i
     }
     FVC_REQUIRE(gather && scatter && offsets_dev, FVC_ERR_RUNTIME, "fvc_conv_wgrad: null CSR pointer");
     WgradArgs a{x, dy, gather, scatter, offsets_host, offsets_dev, nbr, pitch, tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype,
-                grad_w, scratch, scratch_bytes, stream};
+                grad_w, scratch, scratch_bytes, stream, x_is_split != 0, dy_is_split != 0};
     const bool tc_ok = nbr && tc_wgrad_supported(cin, cout, kernel_volume, dtype);
     if (path == 2 && !tc_ok)
         return set_error(FVC_ERR_UNSUPPORTED, "tensor-core wgrad does not admit dtype code %d with channels %d -> %d", dtype, cin, cout);
     if (tc_ok && path != 1)
         return tc_wgrad(a);
+    FVC_REQUIRE(!a.x_split && !a.dy_split, FVC_ERR_UNSUPPORTED, "fvc_conv_wgrad_ex: split rows are a tensor-core (fp32) operand");
     return simt_wgrad(a);
 }
 

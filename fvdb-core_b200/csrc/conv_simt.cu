@@ -92,7 +92,7 @@ conv_os_simt_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *_
 
 template <typename T> static int launch_forward(const ConvArgs &a) {
     const T *x = reinterpret_cast<const T *>(a.x), *w = reinterpret_cast<const T *>(a.w),
-            *bias = reinterpret_cast<const T *>(a.bias);
+            *bias = reinterpret_cast<const T *>(a.epi.bias);
     T *y = reinterpret_cast<T *>(a.y);
     if (a.cout <= 16) {
         constexpr int TN = 16, TM = SIMT_THREADS / (TN / 4) * 4;
@@ -213,10 +213,14 @@ __global__ void wgrad_reduce_kernel(const typename AccOf<T>::type *__restrict__ 
     }
 }
 
+static void chunking_for(int64_t max_n, int64_t *chunk, int64_t *nchunks);
 static void wgrad_chunking(const int64_t *offsets_host, int64_t k3, int64_t *chunk, int64_t *nchunks) {
     int64_t max_n = 0;
     for (int64_t k = 0; k < k3; ++k)
         max_n = offsets_host[k + 1] - offsets_host[k] > max_n ? offsets_host[k + 1] - offsets_host[k] : max_n;
+    chunking_for(max_n, chunk, nchunks);
+}
+static void chunking_for(int64_t max_n, int64_t *chunk, int64_t *nchunks) {
     int64_t c = ceil_div(max_n > 0 ? max_n : 1, 64);
     c = c < 2048 ? 2048 : c;
     c = ceil_div(c, SIMT_KC) * SIMT_KC;
@@ -224,10 +228,11 @@ static void wgrad_chunking(const int64_t *offsets_host, int64_t k3, int64_t *chu
     *nchunks = ceil_div(max_n > 0 ? max_n : 1, c);
 }
 
-size_t simt_wgrad_scratch_bytes(int64_t /*max pairs per tap, unknown here: assume worst case*/, int32_t cin,
-                                int32_t cout, int64_t k3, int32_t dtype) {
+size_t simt_wgrad_scratch_bytes(int64_t max_pairs_per_tap, int32_t cin, int32_t cout, int64_t k3, int32_t dtype) {
     const size_t acc = dtype == FVC_F64 ? 8 : 4;
-    return size_t(64) * size_t(k3) * size_t(cin) * size_t(cout) * acc + 256; // nchunks <= 64
+    int64_t chunk = 0, nchunks = 0;
+    chunking_for(max_pairs_per_tap, &chunk, &nchunks); // the very split launch_wgrad uses (<= 64 chunks)
+    return size_t(nchunks) * size_t(k3) * size_t(cin) * size_t(cout) * acc + 256;
 }
 
 template <typename T> static int launch_wgrad(const WgradArgs &a) {

@@ -308,11 +308,13 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 const int bs = tb % BSTAGES;
                 const uint32_t live = live_units(tile);
                 mbar_wait(bar_bfull + 8 * bs, (tb / BSTAGES) & 1);
+                fence_proxy_async(); // cp.async (generic proxy) wrote the dY tile; tcgen05.mma reads it through the async proxy
                 const uint32_t b_lo = b_lo0 + uint32_t(bs) * (Cfg::B_STAGE >> 4);
                 for (uint32_t rest = live; rest; rest &= rest - 1u) {
                     const int ul = __ffs(rest) - 1;
                     for (int i = 0; i < NS; ++i) {
                         mbar_wait(bar_full + 8 * s, ph);
+                        fence_proxy_async();
                         tc_fence_after();
                         const uint32_t a_lo = a_lo0 + uint32_t(s) * (Cfg::A_STAGE >> 4);
                         for (int jj = 0; jj + i <= (SPLIT ? 2 : 0); ++jj) { // X split i meets dY splits 0 .. 2 - i
@@ -413,19 +415,17 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split
     return p;
 }
 
-// tc_split_rows_kernel lives in conv_tc.cu
-int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t stream);
+// tc_split_rows (conv_tc.cu) writes the bf16 split rows of an fp32 operand
 
 template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1>
 static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, float *partial) {
     using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS>;
     auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT, CTAS>;
     FVC_REQUIRE(CTAS == wgrad_ctas(COUT, SPLIT), FVC_ERR_RUNTIME, "weight-gradient plan / kernel shape mismatch");
-    static bool configured = false;
-    if (!configured) {
-        FVC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0}; // per instantiation, one bit per device
+    const int rc_attr = ensure_dynamic_smem(kernel, Cfg::SMEM, configured);
+    if (rc_attr)
+        return rc_attr;
     const WgradPlan p = plan_wgrad(a.n_out, CIN, COUT, a.k3, SPLIT);
     const uint32_t idesc = make_idesc_f16(128, Cfg::NPAD, SPLIT || a.dtype == FVC_BF16, true, true);
     dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
@@ -462,7 +462,9 @@ size_t tc_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, int32_t 
 
 int tc_wgrad(const WgradArgs &a) {
     const bool split = a.dtype == FVC_F32;
-    const size_t need = tc_wgrad_scratch_bytes(a.n_in, a.n_out, a.cin, a.cout, a.k3, a.dtype);
+    const size_t x_rows = (split && !a.x_split) ? align_up(size_t(a.n_in) * 3 * size_t(a.cin) * 2, 256) : 0;
+    const size_t dy_rows = (split && !a.dy_split) ? align_up(size_t(a.n_out) * 3 * size_t(a.cout) * 2, 256) : 0;
+    const size_t need = wg_partial_bytes(a.n_out, a.cin, a.cout, a.k3, split) + x_rows + dy_rows;
     FVC_REQUIRE(a.scratch && a.scratch_bytes >= need, FVC_ERR_RUNTIME, "tensor-core wgrad scratch too small: %zu < %zu",
                 a.scratch_bytes, need);
     FVC_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 &&
@@ -473,14 +475,19 @@ int tc_wgrad(const WgradArgs &a) {
     float *partial = reinterpret_cast<float *>(a.scratch);
     if (split) {
         uint8_t *base = reinterpret_cast<uint8_t *>(a.scratch) + wg_partial_bytes(a.n_out, a.cin, a.cout, a.k3, true);
-        uint16_t *xs = reinterpret_cast<uint16_t *>(base);
-        uint16_t *dys = reinterpret_cast<uint16_t *>(base + align_up(size_t(a.n_in) * 3 * size_t(a.cin) * 2, 256));
-        int rc = tc_split_rows(reinterpret_cast<const float *>(a.x), a.n_in, a.cin, xs, a.stream);
-        if (rc)
-            return rc;
-        rc = tc_split_rows(reinterpret_cast<const float *>(a.dy), a.n_out, a.cout, dys, a.stream);
-        if (rc)
-            return rc;
+        const void *xs = a.x, *dys = a.dy; // already split by the caller (the rows a layer's forward / dgrad call produced), or split here
+        if (!a.x_split) {
+            const int rc = tc_split_rows(reinterpret_cast<const float *>(a.x), a.n_in, a.cin, reinterpret_cast<uint16_t *>(base), a.stream);
+            if (rc)
+                return rc;
+            xs = base;
+        }
+        if (!a.dy_split) {
+            const int rc = tc_split_rows(reinterpret_cast<const float *>(a.dy), a.n_out, a.cout, reinterpret_cast<uint16_t *>(base + x_rows), a.stream);
+            if (rc)
+                return rc;
+            dys = base + x_rows;
+        }
 #define FVC_WGS_CASE(CI, CO, S)      \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S, true>(a, xs, dys, partial);

@@ -101,9 +101,13 @@ __device__ __forceinline__ void block_column_sum(const float (&vals)[NV], const 
     }
 }
 
-// partial[block][2][C]: per-CTA sum and sum of squares of its rows; counts follow from the row split
+// partial[block][2][C]: per-CTA sum and sum of squares of (x - pivot) over its rows, pivot = row 0 of the batch (shifted
+// sums: with |mean| >> std the plain sum-of-squares form loses the variance to cancellation; around a pivot that is one
+// sample of the distribution the cancellation is relative to ~std).  Counts follow from the row split; CTA 0 also
+// publishes the pivot for the merge kernel.
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const T *__restrict__ x, int64_t n, int c, float *__restrict__ partial) {
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const T *__restrict__ x, int64_t n, int c, float *__restrict__ partial,
+                                                                     float *__restrict__ pivot_out) {
     constexpr int V = RowVec<T>::V;
     __shared__ float smem[BN_THREADS * (2 * V + 1)];
     const Split sp = make_split<T>(c);
@@ -115,12 +119,22 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const T *_
     if (tid < sp.tpb) {
         const int col = tid % sp.cv;
         const int64_t step = int64_t(gridDim.x) * sp.rpb;
+        float pivot[V];
+        RowVec<T>::load(x + col * V, pivot); // n > 0: the host never launches an empty batch
+        if (blockIdx.x == 0 && tid < sp.cv) {
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                pivot_out[col * V + i] = pivot[i];
+        }
         for (int64_t row = int64_t(blockIdx.x) * sp.rpb + tid / sp.cv; row < n; row += BN_UNROLL * step) {
             float v[BN_UNROLL][V]; // BN_UNROLL independent 16-byte loads in flight per thread
 #pragma unroll
             for (int u = 0; u < BN_UNROLL; ++u) {
                 if (row + u * step < n) {
                     RowVec<T>::load(x + (row + u * step) * c + col * V, v[u]);
+#pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        v[u][i] -= pivot[i];
                 } else {
 #pragma unroll
                     for (int i = 0; i < V; ++i)
@@ -164,7 +178,7 @@ __device__ __forceinline__ void chan_merge(double &cnt, double &mu, double &m2, 
 }
 
 __global__ void __launch_bounds__(256)
-bn_stats_final_kernel(const float *__restrict__ partial, int grid, int rpb, int64_t n, int c, float *__restrict__ mean,
+bn_stats_final_kernel(const float *__restrict__ partial, const float *__restrict__ pivot, int grid, int rpb, int64_t n, int c, float *__restrict__ mean,
                       float *__restrict__ var, float *__restrict__ running_mean, float *__restrict__ running_var, float momentum) {
     __shared__ double s_cnt[256], s_mu[256], s_m2[256];
     const int tid = threadIdx.x, lane = tid / FIN_CH, ch = blockIdx.x * FIN_CH + tid % FIN_CH;
@@ -175,10 +189,10 @@ bn_stats_final_kernel(const float *__restrict__ partial, int grid, int rpb, int6
             if (nb == 0.0)
                 continue;
             const double s = partial[(int64_t(b) * 2) * c + ch], ss = partial[(int64_t(b) * 2 + 1) * c + ch];
-            const double mb = s / nb;
+            const double mb = s / nb; // mean of (x - pivot) over the CTA's rows
             double m2b = ss - s * mb;
             m2b = m2b < 0.0 ? 0.0 : m2b;
-            chan_merge(cnt, mu, m2, nb, mb, m2b);
+            chan_merge(cnt, mu, m2, nb, mb + (pivot ? double(pivot[ch]) : 0.0), m2b);
         }
     }
     s_cnt[tid] = cnt, s_mu[tid] = mu, s_m2[tid] = m2;
@@ -413,7 +427,8 @@ using namespace fvc;
 
 extern "C" {
 
-size_t fvc_bn_scratch_bytes(int32_t channels) { return size_t(BN_GRID) * 2 * size_t(channels > 0 ? channels : 0) * sizeof(float) + 256; }
+// [BN_GRID][2][C] CTA partials | [C] pivot row of the statistics pass
+size_t fvc_bn_scratch_bytes(int32_t channels) { return (size_t(BN_GRID) * 2 + 1) * size_t(channels > 0 ? channels : 0) * sizeof(float) + 256; }
 
 int fvc_bn_stats(const void *x, int64_t n, int32_t c, int32_t dtype, float *mean, float *var, float *running_mean, float *running_var,
                  float momentum, void *scratch, size_t scratch_bytes, fvc_stream_t stream_) {
@@ -424,15 +439,34 @@ int fvc_bn_stats(const void *x, int64_t n, int32_t c, int32_t dtype, float *mean
     FVC_REQUIRE(mean && var && scratch && scratch_bytes >= fvc_bn_scratch_bytes(c), FVC_ERR_RUNTIME, "fvc_bn_stats: null output or scratch too small");
     FVC_REQUIRE(n == 0 || x, FVC_ERR_RUNTIME, "fvc_bn_stats: null input");
     float *partial = reinterpret_cast<float *>(scratch);
+    float *pivot = partial + size_t(BN_GRID) * 2 * size_t(c);
     int grid = 1, rpb = 1;
+    if (n == 0) // nothing to launch: the merge kernel writes mean = var = 0 from zero partial counts
+        FVC_CUDA(cudaMemsetAsync(pivot, 0, size_t(c) * sizeof(float), stream));
     FVC_BY_DTYPE(dtype, {
         const Split sp = make_split<T>(c);
         rpb = sp.rpb;
         grid = bn_grid(n, rpb);
-        bn_stats_partial_kernel<T><<<grid, BN_THREADS, 0, stream>>>(reinterpret_cast<const T *>(x), n, c, partial);
+        if (n > 0)
+            bn_stats_partial_kernel<T><<<grid, BN_THREADS, 0, stream>>>(reinterpret_cast<const T *>(x), n, c, partial, pivot);
     });
     FVC_LAUNCH_CHECK();
-    bn_stats_final_kernel<<<int(ceil_div(c, FIN_CH)), 256, 0, stream>>>(partial, grid, rpb, n, c, mean, var, running_mean, running_var, momentum);
+    bn_stats_final_kernel<<<int(ceil_div(c, FIN_CH)), 256, 0, stream>>>(partial, pivot, grid, rpb, n, c, mean, var, running_mean, running_var, momentum);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_bn_stats_from_partials(const float *partial, int64_t blocks, int32_t rows_per_block, int64_t n, int32_t c, float *mean, float *var,
+                               float *running_mean, float *running_var, float momentum, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(c > 0 && mean && var, FVC_ERR_RUNTIME, "fvc_bn_stats_from_partials: null output");
+    FVC_REQUIRE(blocks >= 0 && blocks <= INT32_MAX && rows_per_block > 0 && (blocks == 0 || partial), FVC_ERR_RUNTIME,
+                "fvc_bn_stats_from_partials: bad partial layout");
+    FVC_REQUIRE(n <= blocks * int64_t(rows_per_block) && n > (blocks - 1) * int64_t(rows_per_block), FVC_ERR_RUNTIME,
+                "fvc_bn_stats_from_partials: %lld blocks of %d rows do not cover %lld rows", (long long)blocks, rows_per_block, (long long)n);
+    // block b holds rows [b * rpb, (b + 1) * rpb): with grid == blocks that is exactly the interleaved split of the merge kernel
+    bn_stats_final_kernel<<<int(ceil_div(c, FIN_CH)), 256, 0, stream>>>(partial, nullptr, int(blocks), rows_per_block, n, c, mean, var, running_mean,
+                                                                       running_var, momentum);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }

@@ -30,6 +30,11 @@ def set_conv_path(name: str) -> None:
     _path = _FORCED_PATH[name]
 
 
+def set_kernel_variant(variant: int) -> None:
+    """Benchmark knob (fvc_set_tuning key 0): pipeline-shape variant of the tensor-core forward kernel; 0 = default."""
+    check(lib.fvc_set_tuning(0, int(variant)))
+
+
 def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -474,6 +479,7 @@ def _working_dtype(features: torch.Tensor, weights: torch.Tensor) -> torch.dtype
 
 
 def _pack_weights(weights: torch.Tensor, working: torch.dtype, layout: int, flip_taps: bool = False) -> torch.Tensor:
+    """Public ``[Cout,Cin,k0,k1,k2]`` (any strides) -> ``[K,Cin,Cout]`` (layout 0) / ``[K,Cout,Cin]`` (layout 1) in ``working``."""
     cout, cin, k0, k1, k2 = weights.shape
     out = torch.empty((k0 * k1 * k2, cin, cout) if layout == 0 else (k0 * k1 * k2, cout, cin), dtype=working, device=weights.device)
     strides = (C.c_int64 * 5)(*weights.stride())
@@ -485,25 +491,78 @@ def _pack_weights(weights: torch.Tensor, working: torch.dtype, layout: int, flip
     return out
 
 
-def _run_conv(x: torch.Tensor, w_packed: torch.Tensor, nbr: torch.Tensor, n_in: int, n_out: int, cin: int, cout: int, k3: int,
-              bias: "torch.Tensor | None" = None, tile_mask: "torch.Tensor | None" = None) -> torch.Tensor:
-    device, dtype = x.device, x.dtype
-    y = torch.empty((n_out, cout), dtype=dtype, device=device)
-    if n_out == 0:
-        return y
-    code = _DTYPE_CODE[dtype]
-    scratch_bytes = int(lib.fvc_conv_scratch_bytes(n_in, n_out, cin, cout, k3, code))
-    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
+def _prepare_weights(weights: torch.Tensor, working: torch.dtype, transpose: bool, flip_taps: bool = False) -> torch.Tensor:
+    """The operand the executor consumes (fvc_conv_prepare_weights): ONE launch from the public layout to the tcgen05
+    shared-memory image (or the packed array of the CUDA-core kernels).  ``transpose``: W[k]^T for dgrad."""
+    cout, cin, k0, k1, k2 = (int(v) for v in weights.shape)
+    k3, code = k0 * k1 * k2, _DTYPE_CODE[working]
+    cin_e, cout_e = (cout, cin) if transpose else (cin, cout)
+    nbytes = int(lib.fvc_conv_weights_bytes(cin_e, cout_e, k3, code, _path))
+    blob = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weights.device)
+    strides = (C.c_int64 * 5)(*weights.stride())
     check(
-        lib.fvc_conv_forward(
-            _ptr(x), _ptr(w_packed), _ptr(bias), y.data_ptr(), _ptr(nbr), int(nbr.shape[1]), _ptr(tile_mask), n_in, n_out, cin, cout, k3, code, _path,
-            _ptr(scratch), scratch_bytes, _stream(device),
+        lib.fvc_conv_prepare_weights(
+            _ptr(weights), C.byref(strides), _DTYPE_CODE[weights.dtype], cout, cin, k0, k1, k2, int(transpose), int(flip_taps), code, _path,
+            blob.data_ptr(), nbytes, _stream(weights.device),
         )
     )
-    return y
+    return blob
 
 
-def _forward(features, weights, topo, name, want_transposed, bias=None):
+def split_rows(x: torch.Tensor) -> torch.Tensor:
+    """fp32 rows ``[n, c]`` -> bf16 split rows ``[n, 3, c]`` (fvc_split_rows): the operand of the fp32 tensor-core kernels.  A
+    layer splits its input once and reuses the rows for forward and weight gradient."""
+    n, c = x.shape
+    out = torch.empty((n, 3, c), dtype=torch.bfloat16, device=x.device)
+    if n:
+        check(lib.fvc_split_rows(x.data_ptr(), n, c, out.data_ptr(), _stream(x.device)))
+    return out
+
+
+def _tensor_core_fp32(cin: int, cout: int, k3: int) -> bool:
+    return _path != 1 and int(lib.fvc_conv_scratch_bytes(1, 1, cin, cout, k3, _lib.FVC_F32)) > 0
+
+
+class ConvStats:
+    """Per-block column sums of a convolution output written by the fused epilogue (FvcConvEpilogue.stats)."""
+
+    def __init__(self, partial: torch.Tensor, rows_per_block: int, rows: int):
+        self.partial, self.rows_per_block, self.rows = partial, rows_per_block, rows
+
+
+def _run_conv(x: torch.Tensor, w_prepared: torch.Tensor, nbr: torch.Tensor, n_in: int, n_out: int, cin: int, cout: int, k3: int,
+              bias: "torch.Tensor | None" = None, tile_mask: "torch.Tensor | None" = None, *, dtype: "torch.dtype | None" = None, x_is_split: bool = False,
+              scale: "torch.Tensor | None" = None, shift: "torch.Tensor | None" = None, residual: "torch.Tensor | None" = None, relu: bool = False,
+              want_stats: bool = False):
+    """One output-stationary pass (forward, or dgrad on the reversed map) over prepared weights; optional fused epilogue."""
+    device = x.device
+    dtype = dtype or x.dtype
+    y = torch.empty((n_out, cout), dtype=dtype, device=device)
+    code = _DTYPE_CODE[dtype]
+    stats = None
+    if want_stats:
+        rpb = C.c_int32(0)
+        blocks = int(lib.fvc_conv_stats_blocks(n_out, cin, cout, k3, code, _path, C.byref(rpb)))
+        if rpb.value == 0:
+            raise RuntimeError("fused convolution statistics need the tensor-core path")
+        stats = ConvStats(torch.empty((max(blocks, 1), 2, cout), dtype=torch.float32, device=device), int(rpb.value), n_out)
+    if n_out == 0:
+        return (y, stats) if want_stats else y
+    scratch_bytes = int(lib.fvc_conv_scratch_bytes(n_in, n_out, cin, cout, k3, code)) if (dtype == torch.float32 and not x_is_split) else 0
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
+    epi = _lib.FvcConvEpilogue(_ptr(bias) or None, _ptr(scale) or None, _ptr(shift) or None, _ptr(residual) or None, int(relu),
+                               stats.partial.data_ptr() if stats is not None else None)
+    check(
+        lib.fvc_conv_forward_ex(
+            _ptr(x), int(x_is_split), w_prepared.data_ptr(), C.byref(epi), y.data_ptr(), _ptr(nbr), int(nbr.shape[1]), _ptr(tile_mask), n_in, n_out, cin, cout, k3,
+            code, _path, _ptr(scratch), scratch_bytes, _stream(device),
+        )
+    )
+    return (y, stats) if want_stats else y
+
+
+def _forward(features, weights, topo, name, want_transposed, bias=None, *, features_split=None, scale=None, shift=None, residual=None, relu=False,
+             want_stats=False):
     _check_conv(features, weights, topo, name)
     if topo.is_transposed != want_transposed:
         raise RuntimeError(f"{name} requires topology with direction={'Transposed' if want_transposed else 'Forward'}")
@@ -512,13 +571,25 @@ def _forward(features, weights, topo, name, want_transposed, bias=None):
         features = features.to(working)  # :850-852
     cout, cin = int(weights.shape[0]), int(weights.shape[1])
     with torch.cuda.device(features.device):
-        w = _pack_weights(weights, working, layout=0)
+        w = _prepare_weights(weights, working, transpose=False)
         if bias is not None:
             bias = bias.to(device=features.device, dtype=working).contiguous()
-        return _run_conv(features, w, topo._out_map(), topo.feature_total_voxels, topo.output_total_voxels, cin, cout, topo.kernel_volume, bias, topo._out_mask())
+        if scale is not None:
+            scale = scale.to(device=features.device, dtype=torch.float32).contiguous()
+        if shift is not None:
+            shift = shift.to(device=features.device, dtype=torch.float32).contiguous()
+        if residual is not None:
+            if residual.shape != (topo.output_total_voxels, cout):
+                raise RuntimeError(f"{name}: residual must have shape {(topo.output_total_voxels, cout)}, got {tuple(residual.shape)}")
+            residual = residual.to(working).contiguous()
+        x, x_is_split = features, False
+        if features_split is not None and working == torch.float32:
+            x, x_is_split = features_split, True
+        return _run_conv(x, w, topo._out_map(), topo.feature_total_voxels, topo.output_total_voxels, cin, cout, topo.kernel_volume, bias, topo._out_mask(),
+                         dtype=working, x_is_split=x_is_split, scale=scale, shift=shift, residual=residual, relu=relu, want_stats=want_stats)
 
 
-def _backward(grad_output, features, weights, topo, name, want_transposed, on_grad_weights=None):
+def _backward(grad_output, features, weights, topo, name, want_transposed, on_grad_weights=None, *, features_split=None, need_grad_features=True):
     _check_conv(features, weights, topo, name)
     if topo.is_transposed != want_transposed:
         raise RuntimeError(f"{name} requires {'direction=Transposed' if want_transposed else 'topology with direction=Forward'}")
@@ -541,13 +612,19 @@ def _backward(grad_output, features, weights, topo, name, want_transposed, on_gr
         # wgrad first: dW[k] = X[g]^T . dY[s]  (GatherScatterDefault.cu:806-813).  Its result is the only thing a data-parallel
         # job exchanges, so `on_grad_weights` (e.g. an asynchronous NCCL all-reduce) can overlap the dgrad kernel below.
         grad_weights = torch.empty(tuple(weights.shape), dtype=working, device=device)
-        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, topo.total_pairs, cin, cout, k3, code))
-        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
         offsets_host = topo.offsets
         out_map = topo._out_map()
+        # fp32 on the tensor pipe: X (kept from the forward call when the caller has it) and dY are split ONCE each and the
+        # split rows feed both the weight gradient and dgrad
+        tc32 = working == torch.float32 and n_feat > 0 and n_out > 0 and topo.total_pairs > 0 and _tensor_core_fp32(cin, cout, k3) and _tensor_core_fp32(cout, cin, k3)
+        x_op, x_split = (features_split, 1) if (tc32 and features_split is not None) else (features, 0)
+        dy_op, dy_split = (split_rows(grad_output), 1) if tc32 else (grad_output, 0)
+        max_tap = int((offsets_host[1:] - offsets_host[:-1]).max()) if k3 else 0
+        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, max_tap, cin, cout, k3, code, _path, 1))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
         check(
-            lib.fvc_conv_wgrad(
-                _ptr(features), _ptr(grad_output), _ptr(topo.gather_indices), _ptr(topo.scatter_indices),
+            lib.fvc_conv_wgrad_ex(
+                _ptr(x_op), x_split, _ptr(dy_op), dy_split, _ptr(topo.gather_indices), _ptr(topo.scatter_indices),
                 C.cast(offsets_host.data_ptr(), C.POINTER(C.c_int64)), topo._core.offsets_dev.data_ptr(), _ptr(out_map), int(out_map.shape[1]),
                 _ptr(topo._out_mask()), n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
             )
@@ -555,34 +632,37 @@ def _backward(grad_output, features, weights, topo, name, want_transposed, on_gr
         if on_grad_weights is not None:
             on_grad_weights(grad_weights)
         # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (:803-804), output-stationary over features
-        if n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
+        if not need_grad_features:
+            grad_features = None
+        elif n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
             grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
         else:
             in_map, in_mask, mirror = topo._dgrad_plan()
-            wt = _pack_weights(weights, working, layout=1, flip_taps=mirror)
-            grad_features = _run_conv(grad_output, wt, in_map, n_out, n_feat, cout, cin, k3, None, in_mask)
+            wt = _prepare_weights(weights, working, transpose=True, flip_taps=mirror)
+            grad_features = _run_conv(dy_op, wt, in_map, n_out, n_feat, cout, cin, k3, None, in_mask, dtype=working, x_is_split=bool(dy_split))
     return grad_features, grad_weights
 
 
-def gs_conv(features, weights, topology, bias=None):
-    """Forward sparse convolution (Bindings.cpp:585-594)."""
-    return _forward(features, weights, topology, "gatherScatterDefaultSparseConv", False, bias)
+def gs_conv(features, weights, topology, bias=None, **fused):
+    """Forward sparse convolution (Bindings.cpp:585-594).  Extensions (keyword-only): ``features_split`` (fp32 split rows of
+    ``features``), and the fused block epilogue ``scale`` / ``shift`` / ``residual`` / ``relu`` / ``want_stats``."""
+    return _forward(features, weights, topology, "gatherScatterDefaultSparseConv", False, bias, **fused)
 
 
-def gs_conv_backward(grad_output, features, weights, topology, on_grad_weights=None):
+def gs_conv_backward(grad_output, features, weights, topology, on_grad_weights=None, **extra):
     """(grad_features, grad_weights) of the forward convolution (Bindings.cpp:595-609).  ``on_grad_weights(grad_weights)``
     (extension) is called as soon as the weight gradient is enqueued, before the dgrad kernel."""
-    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvBackward", False, on_grad_weights)
+    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvBackward", False, on_grad_weights, **extra)
 
 
-def gs_conv_transpose(features, weights, topology, bias=None):
+def gs_conv_transpose(features, weights, topology, bias=None, **fused):
     """Forward transposed sparse convolution (Bindings.cpp:627-637)."""
-    return _forward(features, weights, topology, "gatherScatterDefaultSparseConvTranspose", True, bias)
+    return _forward(features, weights, topology, "gatherScatterDefaultSparseConvTranspose", True, bias, **fused)
 
 
-def gs_conv_transpose_backward(grad_output, features, weights, topology, on_grad_weights=None):
+def gs_conv_transpose_backward(grad_output, features, weights, topology, on_grad_weights=None, **extra):
     """(grad_features, grad_weights) of the transposed convolution (Bindings.cpp:638-653)."""
-    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvTransposeBackward", True, on_grad_weights)
+    return _backward(grad_output, features, weights, topology, "gatherScatterDefaultSparseConvTransposeBackward", True, on_grad_weights, **extra)
 
 
 def pred_gather_igemm_conv(features, weights, feature_grid, output_grid, kernel_size: int, stride: int):

@@ -10,7 +10,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "libfvdbconv.so"
 
 FVC_OK, FVC_ERR_VALUE, FVC_ERR_RUNTIME, FVC_ERR_INDEX, FVC_ERR_CUDA, FVC_ERR_UNSUPPORTED = range(6)
 FVC_F16, FVC_BF16, FVC_F32, FVC_F64 = range(4)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FvcGridBatch(C.Structure):
@@ -28,6 +28,10 @@ class FvcGridBatch(C.Structure):
         ("voxel_offsets", C.c_void_p),
         ("leaf_offsets", C.c_void_p),
     ]
+
+
+class FvcConvEpilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p), ("relu", C.c_int32), ("stats", C.c_void_p)]
 
 
 _I3 = C.c_int32 * 3
@@ -62,7 +66,15 @@ SIGNATURES = {
     "fvc_pack_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fvc_conv_scratch_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64, _i32]),
     "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
-    "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i64, _i32]),
+    "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _i32]),
+    "fvc_set_tuning": (C.c_int, [_i32, _i32]),
+    "fvc_conv_weights_bytes": (_sz, [_i32, _i32, _i64, _i32, _i32]),
+    "fvc_conv_prepare_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "fvc_conv_stats_blocks": (_i64, [_i64, _i32, _i32, _i64, _i32, _i32, C.POINTER(_i32)]),
+    "fvc_conv_forward_ex": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
+    "fvc_split_rows": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "fvc_conv_wgrad_ex": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, C.POINTER(_i64), _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fvc_bn_stats_from_partials": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, C.c_float, _vp]),
     "fvc_bn_scratch_bytes": (_sz, [_i32]),
     "fvc_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.c_float, _vp, _sz, _vp]),
     "fvc_bn_apply": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.c_float, _i32, _vp, _vp]),

@@ -78,7 +78,7 @@ class BatchNormFn(torch.autograd.Function):
                     dist.all_gather(gathered, packed, group=group)
                     g = torch.stack(gathered).double()
                     counts = g[:, -1:]
-                    total = counts.sum()
+                    total = counts.sum().clamp_min(1)  # (an all-empty batch normalises nothing)
                     mean64 = (g[:, :c] * counts).sum(0) / total
                     m2 = g[:, c:2 * c].sum(0) + (counts * (g[:, :c] - mean64) ** 2).sum(0)
                     mean, var, count_dev = mean64.float(), (m2 / total).float(), total.float().reshape(1)  # the count stays on the device
@@ -126,11 +126,66 @@ class BatchNormFn(torch.autograd.Function):
         return dx, grad_w, grad_b, None, None, None, None, None, None, None
 
 
+class _SyncBatchNormTorchFn(torch.autograd.Function):
+    """Distributed batch norm in plain torch ops for the shapes the native kernels do not serve (fp64, odd channel counts):
+    same collectives as the native path (one all_gather of (mean, M2, count) forward, one all_reduce of the two sums
+    backward), so every rank of the group -- including a rank with zero rows -- takes part."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, group):  # type: ignore[override]
+        import torch.distributed as dist
+
+        n, c = x.shape
+        xd = x.double()
+        mean_l = xd.mean(0) if n else xd.new_zeros(c)
+        m2_l = ((xd - mean_l) ** 2).sum(0) if n else xd.new_zeros(c)
+        packed = torch.cat([mean_l, m2_l, xd.new_full((1,), float(n))])
+        gathered = [torch.empty_like(packed) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(gathered, packed, group=group)
+        g = torch.stack(gathered)
+        counts = g[:, -1:]
+        total = counts.sum().clamp_min(1)
+        mean = (g[:, :c] * counts).sum(0) / total
+        var = (g[:, c:2 * c].sum(0) + (counts * (g[:, :c] - mean) ** 2).sum(0)) / total
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+            running_var.mul_(1 - momentum).add_((var * total / (total - 1).clamp_min(1)).to(running_var.dtype), alpha=momentum)
+        invstd = torch.rsqrt(var + eps)
+        xhat = (xd - mean) * invstd
+        y = xhat * (weight.double() if weight is not None else 1.0) + (bias.double() if bias is not None else 0.0)
+        if relu:
+            y = torch.relu(y)
+        ctx.save_for_backward(xhat, invstd, weight if weight is not None else x.new_empty(0), (y > 0) if relu else x.new_empty(0), total)
+        ctx.cfg = (group, relu, weight is not None, bias is not None, x.dtype)
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):  # type: ignore[override]
+        import torch.distributed as dist
+
+        xhat, invstd, weight, positive, total = ctx.saved_tensors
+        group, relu, has_w, has_b, dtype = ctx.cfg
+        dz = grad_output.double()
+        if relu:
+            dz = dz * positive
+        local = torch.stack([dz.sum(0), (dz * xhat).sum(0)])
+        sums = local.clone()
+        dist.all_reduce(sums, group=group)
+        gamma = weight.double() if has_w else 1.0
+        dx = (gamma * invstd * (dz - sums[0] / total - xhat * sums[1] / total)).to(dtype)
+        return dx, (local[1].to(weight.dtype) if has_w else None), (local[0].to(dtype) if has_b else None), None, None, None, None, None, None
+
+
 def batch_norm_rows(x, weight, bias, running_mean, running_var, training, momentum, eps, relu=False, group=None):
-    """Functional form used by fvdb.nn.BatchNorm / SyncBatchNorm."""
-    if native_rows_supported(x) and (training or running_mean is not None) and x.shape[0] > 0:
+    """Functional form used by fvdb.nn.BatchNorm / SyncBatchNorm.
+
+    Which implementation runs depends only on rank-invariant properties (dtype, channel count, device): with a process
+    group every rank must reach the same collectives, also a rank that owns zero rows (the by-grid partition leaves ranks
+    empty when there are fewer grids than ranks; torch.nn.SyncBatchNorm, which the reference subclasses, accepts that)."""
+    distributed = group is not None and training
+    if native_rows_supported(x) and (training or running_mean is not None) and (x.shape[0] > 0 or distributed):
         return BatchNormFn.apply(x, weight, bias, running_mean, running_var, training, momentum, eps, relu, group)
-    if group is not None and training:
-        raise RuntimeError("SyncBatchNorm: this shape / dtype / device is not served by the native kernels and has no distributed fallback")
+    if distributed:
+        return _SyncBatchNormTorchFn.apply(x.contiguous(), weight, bias, running_mean, running_var, momentum, eps, relu, group)
     y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)
     return torch.relu(y) if relu else y

@@ -280,16 +280,25 @@ class _GatherScatterConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, weights, bias, topo, transposed):  # type: ignore[override]
         fn = _fvdb_cpp.gs_conv_transpose if transposed else _fvdb_cpp.gs_conv
-        ctx.save_for_backward(features, weights)
+        # fp32 on the tensor pipe: the layer's input is split into its three bf16 parts ONCE; the split rows serve the
+        # forward pass now and the weight gradient later (instead of a 10 B/element pre-pass in each of the two calls)
+        split = None
+        if (features.dtype == torch.float32 and weights.dtype == torch.float32 and features.is_cuda and features.shape[0] > 0
+                and (ctx.needs_input_grad[1] or ctx.needs_input_grad[0])
+                and _fvdb_cpp._tensor_core_fp32(int(weights.shape[1]), int(weights.shape[0]), topo.kernel_volume)):
+            with torch.cuda.device(features.device):
+                split = _fvdb_cpp.split_rows(features.contiguous())
+        ctx.save_for_backward(features, weights, *([split] if split is not None else []))
         ctx.topo, ctx.transposed, ctx.has_bias = topo, transposed, bias is not None
-        return fn(features, weights, topo, bias)
+        return fn(features, weights, topo, bias, features_split=split)
 
     @staticmethod
     def backward(ctx, grad_output):  # type: ignore[override]
-        features, weights = ctx.saved_tensors
+        features, weights, *rest = ctx.saved_tensors
         fn = _fvdb_cpp.gs_conv_transpose_backward if ctx.transposed else _fvdb_cpp.gs_conv_backward
         grad_output = grad_output.contiguous()
-        grad_features, grad_weights = fn(grad_output, features, weights, ctx.topo)
+        grad_features, grad_weights = fn(grad_output, features, weights, ctx.topo, features_split=rest[0] if rest else None,
+                                         need_grad_features=ctx.needs_input_grad[0])
         # bias gradient: fp32 column sums in one streaming pass (csrc/norm.cu), rounded once
         grad_bias = _norm.column_sums(grad_output).to(grad_output.dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return grad_features, grad_weights, grad_bias, None, None

@@ -131,14 +131,15 @@ class GroupNorm(nn.GroupNorm):
             groups, per = self.num_groups, c // self.num_groups
             batches = grid.grid_count
             owner = grid.jidx.long() if batches > 1 else torch.zeros(n, dtype=torch.long, device=x.device)
-            xg = x.float().reshape(n, groups, per)
-            count = torch.zeros(batches, device=x.device).index_add_(0, owner, torch.ones(n, device=x.device)).clamp_min(1.0) * per
-            mean = torch.zeros((batches, groups), device=x.device).index_add_(0, owner, xg.sum(-1)) / count[:, None]
+            work = torch.float64 if x.dtype == torch.float64 else torch.float32  # fp64 inputs keep the reference's fp64 accuracy
+            xg = x.to(work).reshape(n, groups, per)
+            count = torch.zeros(batches, device=x.device, dtype=work).index_add_(0, owner, torch.ones(n, device=x.device, dtype=work)).clamp_min(1.0) * per
+            mean = torch.zeros((batches, groups), device=x.device, dtype=work).index_add_(0, owner, xg.sum(-1)) / count[:, None]
             centred = xg - mean[owner][:, :, None]
-            var = torch.zeros((batches, groups), device=x.device).index_add_(0, owner, centred.square().sum(-1)) / count[:, None]
+            var = torch.zeros((batches, groups), device=x.device, dtype=work).index_add_(0, owner, centred.square().sum(-1)) / count[:, None]
             out = (centred * torch.rsqrt(var + self.eps)[owner][:, :, None]).reshape(n, c)
             if self.affine:
-                out = out * self.weight.float() + self.bias.float()
+                out = out * self.weight.to(work) + self.bias.to(work)
             return grid.jagged_like(out.to(x.dtype))
 
 

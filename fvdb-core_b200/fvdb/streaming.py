@@ -66,7 +66,7 @@ class HostPipelinedConv:
             "gw_chunks": torch.empty((chunks, *weight_shape), dtype=dtype, device=dev),
             "fwd_bytes": int(lib.fvc_conv_scratch_bytes(n, rows, cin, cout, k3, code)),
             "bwd_bytes": int(lib.fvc_conv_scratch_bytes(n, rows, cout, cin, k3, code)),
-            "wg_bytes": int(lib.fvc_conv_wgrad_scratch_bytes(n, rows, topo.total_pairs, cin, cout, k3, code)),
+            "wg_bytes": int(lib.fvc_conv_wgrad_scratch_bytes(n, rows, topo.total_pairs, cin, cout, k3, code, 2, 1)),
             "x_ready": [torch.cuda.Event() for _ in range(chunks)], "dy_ready": [torch.cuda.Event() for _ in range(chunks)],
             "y_done": [torch.cuda.Event() for _ in range(chunks)], "g_done": [torch.cuda.Event() for _ in range(chunks)],
             "final": torch.cuda.Event(),
@@ -78,13 +78,13 @@ class HostPipelinedConv:
         self._ws[key] = ws
         return ws
 
-    def _conv_rows(self, x, w_packed, nbr, mask, r0, r1, cin, cout, out, scratch, scratch_bytes, stream):
+    def _conv_rows(self, x, w_prepared, nbr, mask, r0, r1, cin, cout, out, scratch, scratch_bytes, stream):
         """Rows [r0, r1) of the output-stationary kernel: map, tile mask and output are offset by the chunk's first row."""
         k3, pitch = int(nbr.shape[0]), int(nbr.stride(0))
         words = (k3 + 63) // 64
         check(
-            lib.fvc_conv_forward(
-                x.data_ptr(), w_packed.data_ptr(), None, out.data_ptr() + r0 * cout * out.element_size(), nbr.data_ptr() + 4 * r0, pitch,
+            lib.fvc_conv_forward_ex(
+                x.data_ptr(), 0, w_prepared.data_ptr(), None, out.data_ptr() + r0 * cout * out.element_size(), nbr.data_ptr() + 4 * r0, pitch,
                 (mask.data_ptr() + 8 * words * (r0 // 128)) if mask is not None else None, int(x.shape[0]), r1 - r0, cin, cout, k3,
                 cpp._DTYPE_CODE[x.dtype], 2, scratch.data_ptr(), scratch_bytes, stream,
             )
@@ -121,7 +121,11 @@ class HostPipelinedConv:
         in_map, in_mask, mirror = topo._dgrad_plan()
         out_map, out_mask = topo._out_map(), topo._out_mask()
         with torch.cuda.device(dev):
-            w_fwd, w_bwd = cpp._pack_weights(weights, dtype, 0), cpp._pack_weights(weights, dtype, 1, flip_taps=mirror)
+            prev_path, cpp._path = cpp._path, 2  # the chunk calls force the tensor-core family: prepare its operand
+            try:  # ONE weight image per direction and step, shared by every chunk
+                w_fwd, w_bwd = cpp._prepare_weights(weights, dtype, False), cpp._prepare_weights(weights, dtype, True, flip_taps=mirror)
+            finally:
+                cpp._path = prev_path
             self.s_in.wait_stream(main)  # the previous step's kernels are done with x / dy before they are overwritten
             self.s_out.wait_stream(main)
             with torch.cuda.stream(self.s_in):  # uploads in the order the kernels need them

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FVC_ABI_VERSION 2
+#define FVC_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FVC_API __attribute__((visibility("default")))
@@ -94,6 +94,10 @@ FVC_API const char *fvc_last_error(void);
 FVC_API int fvc_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 FVC_API int64_t fvc_launch_count(void);
+
+/* Experiment knob for the benchmark scripts: key 0 = pipeline-shape variant of the tensor-core forward kernel
+ * (0 = the shape table's default).  Not part of the reference interface. */
+FVC_API int fvc_set_tuning(int32_t key, int32_t value);
 
 /* -------- geometry (host-only; replaces ConvolutionGeometry.h:30-207) ----------------------------- */
 /* Validates kernel_size / stride (> 0, volume fits int64) and returns padding_before / padding_after /
@@ -208,18 +212,61 @@ FVC_API size_t fvc_conv_scratch_bytes(int64_t n_in, int64_t n_out, int32_t cin, 
 FVC_API int fvc_conv_forward(const void *x, const void *w_packed, const void *bias, void *y, const int32_t *nbr, int64_t pitch,
                      const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype,
                      int32_t path, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
+/* ---- prepared weights + fused block epilogue (bias + BatchNorm-apply + ReLU + residual in
+ *      the GEMM epilogue, fvdb/nn/modules.py:484-521, fvdb/nn/simple_unet.py:233-243) ---------------------------------
+ * fvc_conv_prepare_weights writes, in ONE launch from the public [Cout,Cin,k0,k1,k2] tensor (any strides), the operand the
+ * executor chosen by (dtype, channels, path) consumes: the pre-swizzled shared-memory image of the tcgen05 kernels (fp32:
+ * its three-way bf16 split) or the packed [K][Cin][Cout] array of the CUDA-core kernels.  transpose != 0 prepares W[k]^T
+ * (dgrad); flip_taps as in fvc_pack_weights.  The blob can be cached for as long as the weights do not change.
+ * fvc_conv_weights_bytes takes the EXECUTOR's channel counts (dgrad: cin = public Cout, cout = public Cin). */
+FVC_API size_t fvc_conv_weights_bytes(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path);
+FVC_API int fvc_conv_prepare_weights(const void *weights, const int64_t strides[5], int32_t dtype_in, int32_t cout, int32_t cin, int32_t k0,
+                                     int32_t k1, int32_t k2, int32_t transpose, int32_t flip_taps, int32_t dtype, int32_t path, void *prepared,
+                                     size_t prepared_bytes, fvc_stream_t stream);
+/* stored[o,c] = act(((acc[o,c] + bias[c]) * scale[c] + shift[c]) + residual[o,c]); every member may be NULL / 0.
+ * bias / residual in `dtype`, scale / shift fp32 (an eval-mode BatchNorm folds into them).  stats: fp32
+ * [fvc_conv_stats_blocks()][2][Cout], per block of rows_per_block consecutive output rows the column sums and sums of squares
+ * of the STORED values (what a BatchNorm statistics pass over y would read) -- written, not accumulated; deterministic.
+ * scale / shift / residual / relu / stats need the tensor-core path (FVC_ERR_UNSUPPORTED otherwise). */
+typedef struct FvcConvEpilogue {
+    const void *bias;
+    const float *scale;
+    const float *shift;
+    const void *residual;
+    int32_t relu;
+    float *stats;
+} FvcConvEpilogue;
+FVC_API int64_t fvc_conv_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path,
+                                      int32_t *rows_per_block);
+/* fvc_conv_forward over prepared weights.  x_is_split != 0 (fp32 only): x holds the bf16 split rows fvc_split_rows wrote
+ * ([n_in][3][Cin] bf16) -- a layer splits its input once and reuses the rows for forward and wgrad.  scratch: only for fp32
+ * with x_is_split == 0 (fvc_conv_scratch_bytes is always enough). */
+FVC_API int fvc_conv_forward_ex(const void *x, int32_t x_is_split, const void *w_prepared, const FvcConvEpilogue *epilogue, void *y,
+                                const int32_t *nbr, int64_t pitch, const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin,
+                                int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, void *scratch, size_t scratch_bytes,
+                                fvc_stream_t stream);
+/* fp32 rows [n][channels] -> bf16 split rows [n][3][channels] (x = s0 + s1 + s2 exactly to 24 bits); channels % 8 == 0 */
+FVC_API int fvc_split_rows(const float *x, int64_t n, int32_t channels, void *split_rows, fvc_stream_t stream);
+
 /* Weight gradient: grad_w[co][ci][k0][k1][k2] = sum over pairs p of tap k of x[gather[p]][ci] * dy[scatter[p]][co]
  * (GatherScatterDefault.cu:806-813), written contiguous in the public layout in `dtype`;
  * fixed-order (deterministic) fp32/fp64 reduction.  offsets_host / offsets_dev: the same int64 [K^3+1]
  * CSR offsets on the host and on the device.  nbr/pitch: the output-stationary dense map of the same
  * rulebook (used by the tensor-core path; may be NULL, then the CSR path runs). */
-FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t total_pairs, int32_t cin, int32_t cout,
-                                    int64_t kernel_volume, int32_t dtype);
+/* Scratch for the kernel family fvc_conv_wgrad will take: max_pairs_per_tap = the largest CSR tap segment (sizes the
+ * CUDA-core partials), path as in the call, has_dense_map = whether nbr will be passed. */
+FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t max_pairs_per_tap, int32_t cin, int32_t cout,
+                                    int64_t kernel_volume, int32_t dtype, int32_t path, int32_t has_dense_map);
 FVC_API int fvc_conv_wgrad(const void *x, const void *dy, const int32_t *gather, const int32_t *scatter,
                    const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
                    const uint64_t *tile_mask, int64_t n_in, int64_t n_out,
                    int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, void *grad_w,
                    void *scratch, size_t scratch_bytes, fvc_stream_t stream);
+/* Same, with fp32 operands optionally passed as the bf16 split rows of fvc_split_rows (x: [n_in][3][Cin], dy: [n_out][3][Cout]). */
+FVC_API int fvc_conv_wgrad_ex(const void *x, int32_t x_is_split, const void *dy, int32_t dy_is_split, const int32_t *gather,
+                      const int32_t *scatter, const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
+                      const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume,
+                      int32_t dtype, int32_t path, void *grad_w, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
 
 /* -------- stride-1 generated topologies by leaf-mask morphology (fast path of conv_grid / conv_transpose_grid;
  *          replaces the NanoVDB DilateGrid route of ops/BuildGridForConv.cu:392-463) --------------------------------
@@ -244,6 +291,10 @@ FVC_API size_t fvc_bn_scratch_bytes(int32_t channels);
 FVC_API int fvc_bn_stats(const void *x, int64_t n, int32_t channels, int32_t dtype, float *mean, float *var, float *running_mean,
                  float *running_var, float momentum, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
 /* y = act((x - mean) / sqrt(var + eps) * gamma + beta), act = ReLU when relu != 0 */
+/* Same statistics from the per-block column sums the convolution epilogue wrote (FvcConvEpilogue.stats): partial
+ * [blocks][2][channels], block b covering rows [b * rows_per_block, min(n, (b + 1) * rows_per_block)). */
+FVC_API int fvc_bn_stats_from_partials(const float *partial, int64_t blocks, int32_t rows_per_block, int64_t n, int32_t channels, float *mean,
+                               float *var, float *running_mean, float *running_var, float momentum, fvc_stream_t stream);
 FVC_API int fvc_bn_apply(const void *x, int64_t n, int32_t channels, int32_t dtype, const float *mean, const float *var, const float *gamma,
                  const float *beta, float eps, int32_t relu, void *y, fvc_stream_t stream);
 /* sums[0][c] = sum dz (= grad beta), sums[1][c] = sum dz * xhat (= grad gamma); dz = dy masked by the fused ReLU */

@@ -148,6 +148,20 @@ class CoordIndex:
             dup = np.all(self._sorted[1:] == self._sorted[:-1], axis=1)
             if dup.any():
                 raise ValueError("coordinate table contains duplicate (batch, ijk) rows")
+        # Fast path (full-size parity cases): when the table's bounding box fits 62 bits, (b, i, j, k) packs into ONE
+        # int64 key whose order equals the lexicographic order, so a lookup is a plain integer binary search.  Queries
+        # outside the box are misses by construction.  Same answers as the structured path (tests/test_oracle_golden.py).
+        self._packed = None
+        if self.n > 0:
+            lo = self._sorted.min(axis=0)
+            span = self._sorted.max(axis=0) - lo + 1
+            if float(span[0]) * float(span[1]) * float(span[2]) * float(span[3]) < 2.0**62:
+                self._lo, self._span = lo, span
+                self._packed = self._pack(self._sorted)
+
+    def _pack(self, table: np.ndarray) -> np.ndarray:
+        rel = table - self._lo
+        return ((rel[:, 0] * self._span[1] + rel[:, 1]) * self._span[2] + rel[:, 2]) * self._span[3] + rel[:, 3]
 
     def lookup(self, bidx: np.ndarray, ijk: np.ndarray) -> np.ndarray:
         ijk = np.asarray(ijk, dtype=np.int64).reshape(-1, 3)
@@ -156,6 +170,15 @@ class CoordIndex:
         if self.n == 0 or ijk.shape[0] == 0:
             return out
         query = np.ascontiguousarray(np.concatenate([bidx[:, None], ijk], axis=1))
+        if self._packed is not None:
+            inside = np.all((query >= self._lo) & (query < self._lo + self._span), axis=1)
+            keys = self._pack(query[inside])
+            pos = np.minimum(np.searchsorted(self._packed, keys), self.n - 1)
+            hit = self._packed[pos] == keys
+            rows = np.full(keys.shape[0], -1, dtype=np.int64)
+            rows[hit] = self._rows[pos[hit]]
+            out[inside] = rows
+            return out
         qview = query.view(self._view.dtype).reshape(-1)
         pos = np.searchsorted(self._view, qview)
         pos_c = np.minimum(pos, self.n - 1)
@@ -224,18 +247,27 @@ def build_topology(feat_ijk, feat_bidx, out_ijk, out_bidx, kernel_size, stride, 
     n_out = int(np.asarray(out_ijk).reshape(-1, 3).shape[0])
     if n_feat > _INT32_MAX or n_out > _INT32_MAX:  # :68-80
         raise RuntimeError("voxel count exceeds the int32 index limit")
-    nbr = dense_kernel_map(feat_ijk, feat_bidx, out_ijk, out_bidx, kernel_size, stride, transposed)
+    # one tap at a time (the dense [n_out, K] form of a 5^3 map over millions of voxels would not fit comfortably)
     K = geometry.kernel_volume
-    counts = (nbr >= 0).sum(axis=0).astype(np.int64) if n_out else np.zeros(K, dtype=np.int64)
-    offsets = np.zeros(K + 1, dtype=np.int64)
-    offsets[1:] = np.cumsum(counts)  # :145-151
-    total = int(offsets[K])
-    gather = np.empty(total, dtype=np.int32)
-    scatter = np.empty(total, dtype=np.int32)
+    out_ijk_ = np.asarray(out_ijk, dtype=np.int64).reshape(-1, 3)
+    out_bidx_ = np.asarray(out_bidx, dtype=np.int64).reshape(-1)
+    index = CoordIndex(feat_ijk, feat_bidx)
+    per_tap = []
     for k in range(K):
-        out_rows = np.nonzero(nbr[:, k] >= 0)[0]
-        gather[offsets[k] : offsets[k + 1]] = nbr[out_rows, k]
-        scatter[offsets[k] : offsets[k + 1]] = out_rows
+        tap = geometry.tap_coord(k)
+        if transposed:  # :129-141
+            probe, ok = geometry.coarse_from_fine(out_ijk_, tap)
+            rows = index.lookup(out_bidx_, probe)
+            rows[~ok] = -1
+        else:
+            rows = index.lookup(out_bidx_, geometry.fine_from_coarse(out_ijk_, tap))
+        out_rows = np.nonzero(rows >= 0)[0]
+        per_tap.append((rows[out_rows].astype(np.int32), out_rows.astype(np.int32)))
+    offsets = np.zeros(K + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum([len(g) for g, _ in per_tap])  # :145-151
+    total = int(offsets[K])
+    gather = np.concatenate([g for g, _ in per_tap]) if total else np.empty(0, dtype=np.int32)
+    scatter = np.concatenate([s for _, s in per_tap]) if total else np.empty(0, dtype=np.int32)
     return Topology(gather, scatter, offsets, n_feat, n_out, K, total, geometry.kernel_size, geometry.stride, bool(transposed))
 
 

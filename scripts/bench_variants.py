@@ -1,10 +1,24 @@
-"""Times the forward tcgen05 kernel on the C2 workload for each FVC_TC_VARIANT (pipeline-shape experiment)."""
-import os, sys, json
-sys.path.insert(0, "fvdb-core_b200"); sys.path.insert(0, ".")
-import torch, fvdb, bench
+"""Times the forward tcgen05 kernel for each pipeline-shape variant (fvc_set_tuning key 0) on a bench workload.
+
+    python scripts/bench_variants.py [config=c2] [variants=0,1,2,...] [out.json]
+
+variant 1 = the round-1 kernel (four producer warps sharing every unit + map ring); the others are warp-per-unit
+shapes (csrc/conv_tc.cu: tc_forward_half).  Every variant's output is compared with variant 1's (bit-equal expected:
+same MMA order per accumulator).  L2 is flushed between timed launches? No -- inputs (features + map) exceed L2.
+"""
+import json
+import sys
+
+sys.path.insert(0, "fvdb-core_b200")
+sys.path.insert(0, ".")
+import torch
+
+import bench
+import fvdb
 from fvdb import _fvdb_cpp as cpp
 
 cfg = bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
+variants = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "1,0,2,3,4,5,6").split(",")]
 dev = torch.device("cuda")
 coords = bench.make_coords(cfg, 0, dev)
 grid = fvdb.GridBatch.from_ijk(fvdb.JaggedTensor(coords))
@@ -14,15 +28,32 @@ n, k3, cin, cout = grid.total_voxels, topo.kernel_volume, cfg["cin"], cfg["cout"
 dtype = bench.DTYPES[cfg["dtype"]]
 x = torch.randn((n, cin), device=dev).to(dtype)
 w = (torch.randn((cout, cin, cfg["kernel"], cfg["kernel"], cfg["kernel"]), device=dev) * 0.02).to(dtype)
-wp = cpp._pack_weights(w, dtype, 0)
-ref = None
-for variant in [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,1,2,3,10".split(","))]:
-    os.environ["FVC_TC_VARIANT"] = str(variant)
-    f = lambda: cpp._run_conv(x, wp, topo._out_map(), n, n, cin, cout, k3, None, topo._out_mask())
-    y = f(); torch.cuda.synchronize()
-    if ref is None: ref = y
+wp = cpp._prepare_weights(w, dtype, False)
+ref, rows = None, []
+for variant in variants:
+    cpp.set_kernel_variant(variant)
+    f = lambda: cpp._run_conv(x, wp, topo._out_map(), n, n, cin, cout, k3, None, topo._out_mask())  # noqa: E731
+    try:
+        y = f()
+        torch.cuda.synchronize()
+    except RuntimeError as exc:
+        rows.append({"variant": variant, "error": str(exc)[:200]})
+        print(json.dumps(rows[-1]), flush=True)
+        continue
+    if ref is None:
+        ref = y
+    for _ in range(3):
+        f()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(5): f()
-    b.record(); torch.cuda.synchronize()
-    print(json.dumps({"variant": variant, "fwd_ms": a.elapsed_time(b) / 5, "max_abs_diff_vs_v0": float((y.float() - ref.float()).abs().max())}), flush=True)
+    for _ in range(10):
+        f()
+    b.record()
+    torch.cuda.synchronize()
+    rows.append({"config": cfg["desc"], "variant": variant, "fwd_ms": a.elapsed_time(b) / 10, "max_abs_diff_vs_first": float((y.float() - ref.float()).abs().max())})
+    print(json.dumps(rows[-1]), flush=True)
+cpp.set_kernel_variant(0)
+if len(sys.argv) > 3:
+    with open(sys.argv[3], "w") as fh:
+        json.dump(rows, fh, indent=1)

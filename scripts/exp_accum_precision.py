@@ -24,7 +24,7 @@ for mode in ("randn", "positive"):
         x, dy = x.abs(), dy.abs()
     x, dy = x.bfloat16(), dy.bfloat16()
     code = cpp._DTYPE_CODE[torch.bfloat16]
-    sb = int(lib.fvc_conv_wgrad_scratch_bytes(n, n, topo.total_pairs, cin, cout, k3, code))
+    sb = int(lib.fvc_conv_wgrad_scratch_bytes(n, n, topo.total_pairs, cin, cout, k3, code, 0, 1))
     scratch = torch.zeros(sb, dtype=torch.uint8, device=dev)
     gw = torch.empty((cout, cin, 3, 3, 3), dtype=torch.bfloat16, device=dev)
     out_map = topo._out_map()

@@ -28,7 +28,7 @@ def test_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(str(REPO / "fvdb-core_b200" / "fvdb" / "libfvdbconv.so"))
     for name in declared:
         assert hasattr(lib, name), f"libfvdbconv.so does not export {name}"
-    assert _lib.lib.fvc_abi_version() == 2
+    assert _lib.lib.fvc_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_geometry_entry_points_match_oracle_and_reference_kats():
