@@ -5,7 +5,8 @@
 namespace fvc {
 
 // Fused epilogue of the forward / dgrad kernels (FvcConvEpilogue in the ABI); every member optional.
-// stored = act(((acc + bias) * scale + shift) + residual); stats = per-CTA column sums of the stored values.
+// stored = act2(act1((acc + bias) * scale + shift) + residual), act1 / act2 = ReLU when bit 0 / bit 1 of `relu` is set;
+// stats = per-CTA column sums of the stored values.
 struct Epilogue {
     const void *bias = nullptr;     // [Cout] in `dtype`
     const float *scale = nullptr;   // [Cout] fp32

@@ -623,6 +623,11 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                             a += __ldg(epi.shift + c0 + z);
                         v[z] = a;
                     }
+                    if (epi.relu & 1) { // the block's activation (before a skip connection joins)
+#pragma unroll
+                        for (int z = 0; z < EC; ++z)
+                            v[z] = fmaxf(v[z], 0.f);
+                    }
                     if (epi.residual && row_ok) {
                         if (SPLIT) {
                             const float4 *res = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(epi.residual) + row * COUT + c0);
@@ -646,7 +651,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                             }
                         }
                     }
-                    if (epi.relu) {
+                    if (epi.relu & 2) { // activation after the skip connection (fvdb/nn/simple_unet.py:187-188)
 #pragma unroll
                         for (int z = 0; z < EC; ++z)
                             v[z] = fmaxf(v[z], 0.f);

@@ -532,9 +532,10 @@ class ConvStats:
 
 def _run_conv(x: torch.Tensor, w_prepared: torch.Tensor, nbr: torch.Tensor, n_in: int, n_out: int, cin: int, cout: int, k3: int,
               bias: "torch.Tensor | None" = None, tile_mask: "torch.Tensor | None" = None, *, dtype: "torch.dtype | None" = None, x_is_split: bool = False,
-              scale: "torch.Tensor | None" = None, shift: "torch.Tensor | None" = None, residual: "torch.Tensor | None" = None, relu: bool = False,
+              scale: "torch.Tensor | None" = None, shift: "torch.Tensor | None" = None, residual: "torch.Tensor | None" = None, relu: "bool | int" = False,
               want_stats: bool = False):
-    """One output-stationary pass (forward, or dgrad on the reversed map) over prepared weights; optional fused epilogue."""
+    """One output-stationary pass (forward, or dgrad on the reversed map) over prepared weights; optional fused epilogue
+    ``act2(act1((acc + bias) * scale + shift) + residual)``: ``relu`` = True / 1 -> act1 (before the residual), 2 -> act2 (after), 3 -> both."""
     device = x.device
     dtype = dtype or x.dtype
     y = torch.empty((n_out, cout), dtype=dtype, device=device)

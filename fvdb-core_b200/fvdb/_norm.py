@@ -52,11 +52,28 @@ def column_sums(x: torch.Tensor) -> torch.Tensor:
     return sums
 
 
+def stats_from_conv_partials(stats, running_mean=None, running_var=None, momentum: float = 0.0):
+    """(mean, biased var) over the rows of a convolution output from the per-block column sums its fused epilogue wrote
+    (``_fvdb_cpp.ConvStats``): the BatchNorm statistics pass without reading ``y`` again.  Optionally updates fp32 running
+    statistics in place like ``fvc_bn_stats``."""
+    partial = stats.partial
+    c = int(partial.shape[2])
+    mean = torch.empty(c, dtype=torch.float32, device=partial.device)
+    var = torch.empty(c, dtype=torch.float32, device=partial.device)
+    blocks = (stats.rows + stats.rows_per_block - 1) // stats.rows_per_block
+    with torch.cuda.device(partial.device):
+        check(lib.fvc_bn_stats_from_partials(partial.data_ptr(), blocks, stats.rows_per_block, stats.rows, c, mean.data_ptr(), var.data_ptr(),
+                                             _p(running_mean), _p(running_var), float(momentum), torch.cuda.current_stream(partial.device).cuda_stream))
+    return mean, var
+
+
 class BatchNormFn(torch.autograd.Function):
     """y = act(batch_norm(x)); statistics over the rows of this process, or of every process of ``group`` (SyncBatchNorm)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu, group):  # type: ignore[override]
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu, group, conv_stats=None):  # type: ignore[override]
+        """``conv_stats``: the column sums the producing convolution's epilogue wrote for ``x`` (``_fvdb_cpp.ConvStats``); the
+        statistics pass over ``x`` is skipped."""
         n, c = x.shape
         code = _CODES[x.dtype]
         gamma, beta = _f32(weight), _f32(bias)
@@ -68,8 +85,13 @@ class BatchNormFn(torch.autograd.Function):
                 mean = torch.empty(c, dtype=torch.float32, device=x.device)
                 var = torch.empty(c, dtype=torch.float32, device=x.device)
                 in_place = group is None and running_mean is not None and running_mean.dtype == torch.float32 and running_var.dtype == torch.float32
-                check(lib.fvc_bn_stats(x.data_ptr(), n, c, code, mean.data_ptr(), var.data_ptr(), _p(running_mean) if in_place else 0,
-                                       _p(running_var) if in_place else 0, float(momentum), scratch.data_ptr(), scratch.numel(), stream))
+                if conv_stats is not None and n > 0:
+                    blocks = (conv_stats.rows + conv_stats.rows_per_block - 1) // conv_stats.rows_per_block
+                    check(lib.fvc_bn_stats_from_partials(conv_stats.partial.data_ptr(), blocks, conv_stats.rows_per_block, n, c, mean.data_ptr(), var.data_ptr(),
+                                                         _p(running_mean) if in_place else 0, _p(running_var) if in_place else 0, float(momentum), stream))
+                else:
+                    check(lib.fvc_bn_stats(x.data_ptr(), n, c, code, mean.data_ptr(), var.data_ptr(), _p(running_mean) if in_place else 0,
+                                           _p(running_var) if in_place else 0, float(momentum), scratch.data_ptr(), scratch.numel(), stream))
                 if group is not None:  # merge (count, mean, M2) of every rank
                     import torch.distributed as dist
 
@@ -123,7 +145,7 @@ class BatchNormFn(torch.autograd.Function):
                                                 int(training), sums.data_ptr(), count, count_dev.data_ptr() if count_dev.numel() else 0, dx.data_ptr(), stream))
         grad_w = local[1].to(w_dtype) if has_w and ctx.needs_input_grad[1] else None
         grad_b = local[0].to(b_dtype) if has_b and ctx.needs_input_grad[2] else None
-        return dx, grad_w, grad_b, None, None, None, None, None, None, None
+        return dx, grad_w, grad_b, None, None, None, None, None, None, None, None
 
 
 class _SyncBatchNormTorchFn(torch.autograd.Function):
@@ -176,7 +198,7 @@ class _SyncBatchNormTorchFn(torch.autograd.Function):
         return dx, (local[1].to(weight.dtype) if has_w else None), (local[0].to(dtype) if has_b else None), None, None, None, None, None, None
 
 
-def batch_norm_rows(x, weight, bias, running_mean, running_var, training, momentum, eps, relu=False, group=None):
+def batch_norm_rows(x, weight, bias, running_mean, running_var, training, momentum, eps, relu=False, group=None, conv_stats=None):
     """Functional form used by fvdb.nn.BatchNorm / SyncBatchNorm.
 
     Which implementation runs depends only on rank-invariant properties (dtype, channel count, device): with a process
@@ -184,7 +206,7 @@ def batch_norm_rows(x, weight, bias, running_mean, running_var, training, moment
     empty when there are fewer grids than ranks; torch.nn.SyncBatchNorm, which the reference subclasses, accepts that)."""
     distributed = group is not None and training
     if native_rows_supported(x) and (training or running_mean is not None) and (x.shape[0] > 0 or distributed):
-        return BatchNormFn.apply(x, weight, bias, running_mean, running_var, training, momentum, eps, relu, group)
+        return BatchNormFn.apply(x, weight, bias, running_mean, running_var, training, momentum, eps, relu, group, conv_stats if training else None)
     if distributed:
         return _SyncBatchNormTorchFn.apply(x.contiguous(), weight, bias, running_mean, running_var, momentum, eps, relu, group)
     y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)

@@ -278,7 +278,9 @@ class _GatherScatterConvFn(torch.autograd.Function):
     """autograd glue over gs_conv / gs_conv_backward (either direction); an optional bias is added in the kernel epilogue."""
 
     @staticmethod
-    def forward(ctx, features, weights, bias, topo, transposed):  # type: ignore[override]
+    def forward(ctx, features, weights, bias, topo, transposed, stats_out=None):  # type: ignore[override]
+        """``stats_out`` (a dict, extension): the kernel epilogue also writes per-block column sums of the stored output; the
+        ``_fvdb_cpp.ConvStats`` lands in ``stats_out["stats"]`` (not differentiable: it feeds BatchNorm statistics)."""
         fn = _fvdb_cpp.gs_conv_transpose if transposed else _fvdb_cpp.gs_conv
         # fp32 on the tensor pipe: the layer's input is split into its three bf16 parts ONCE; the split rows serve the
         # forward pass now and the weight gradient later (instead of a 10 B/element pre-pass in each of the two calls)
@@ -290,6 +292,10 @@ class _GatherScatterConvFn(torch.autograd.Function):
                 split = _fvdb_cpp.split_rows(features.contiguous())
         ctx.save_for_backward(features, weights, *([split] if split is not None else []))
         ctx.topo, ctx.transposed, ctx.has_bias = topo, transposed, bias is not None
+        if stats_out is not None:
+            y, stats = fn(features, weights, topo, bias, features_split=split, want_stats=True)
+            stats_out["stats"] = stats
+            return y
         return fn(features, weights, topo, bias, features_split=split)
 
     @staticmethod
@@ -301,7 +307,7 @@ class _GatherScatterConvFn(torch.autograd.Function):
                                          need_grad_features=ctx.needs_input_grad[0])
         # bias gradient: fp32 column sums in one streaming pass (csrc/norm.cu), rounded once
         grad_bias = _norm.column_sums(grad_output).to(grad_output.dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return grad_features, grad_weights, grad_bias, None, None
+        return grad_features, grad_weights, grad_bias, None, None, None
 
 
 class _CoverageReportCache:
@@ -451,6 +457,41 @@ class ConvolutionPlan:
         if topology is None:
             raise TypeError(f"Unknown backend type: {type(backend)}")
         out = _GatherScatterConvFn.apply(features, weights, bias, topology, self._transposed)
+        return out if is_flat else self._target_grid.jagged_like(out)
+
+    def fused_epilogue_available(self, features: torch.Tensor, weights: torch.Tensor) -> bool:
+        """Whether ``execute_with_stats`` / ``execute_inference`` can run for these operands: a kernel-map plan on CUDA whose
+        (dtype, channels, kernel volume) the tensor-core executor admits (the fused block epilogue lives there)."""
+        topology = _backend_topology(self._backend)
+        if topology is None or isinstance(self._backend, _MatmulBackend) or not features.is_cuda or weights.ndim != 5:
+            return False
+        working = torch.result_type(features, weights)
+        if working not in _fvdb_cpp._DTYPE_CODE or _fvdb_cpp._path == 1:
+            return False
+        return int(_fvdb_cpp.lib.fvc_conv_scratch_bytes(1, 1, int(weights.shape[1]), int(weights.shape[0]), topology.kernel_volume, _fvdb_cpp._DTYPE_CODE[working])) > 0
+
+    def execute_with_stats(self, data: JaggedTensor | torch.Tensor, weights: torch.Tensor, bias: torch.Tensor | None = None):
+        """``execute`` (differentiable) that also returns the per-block column sums of the output written by the kernel
+        epilogue (``_fvdb_cpp.ConvStats``): a following BatchNorm takes its batch statistics from them instead of reading
+        the output again (reference composition fvdb/nn/modules.py:484-521)."""
+        is_flat = isinstance(data, torch.Tensor)
+        features = data if is_flat else data.jdata
+        holder: dict = {}
+        out = _GatherScatterConvFn.apply(features, weights, bias, _backend_topology(self._backend), self._transposed, holder)
+        return (out if is_flat else self._target_grid.jagged_like(out)), holder["stats"]
+
+    def execute_inference(self, data: JaggedTensor | torch.Tensor, weights: torch.Tensor, bias: torch.Tensor | None = None, *, scale=None, shift=None,
+                          residual=None, relu: "bool | int" = False):
+        """Forward only (no autograd): ``act2(act1((conv(x) + bias) * scale + shift) + residual)`` in ONE kernel -- an eval-mode
+        BatchNorm folds into ``scale`` / ``shift`` (fp32 ``[Cout]``), the block's ReLU (``relu`` bit 0: act1), the skip connection
+        and the ReLU after it (bit 1: act2; fvdb/nn/simple_unet.py:187-188) into the epilogue."""
+        is_flat = isinstance(data, torch.Tensor)
+        features = (data if is_flat else data.jdata).detach()
+        res = None if residual is None else (residual if isinstance(residual, torch.Tensor) else residual.jdata).detach()
+        fn = _fvdb_cpp.gs_conv_transpose if self._transposed else _fvdb_cpp.gs_conv
+        with torch.no_grad():
+            out = fn(features, weights.detach(), _backend_topology(self._backend), None if bias is None else bias.detach(), scale=scale, shift=shift,
+                     residual=res, relu=relu)
         return out if is_flat else self._target_grid.jagged_like(out)
 
     # ---- properties -----------------------------------------------------------------------

@@ -1,4 +1,4 @@
-from .modules import AvgPool, BatchNorm, GroupNorm, MaxPool, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm, UpsamplingNearest
+from .modules import AvgPool, BatchNorm, GroupNorm, MaxPool, conv_bn_act, SparseConv3d, SparseConvTranspose3d, SyncBatchNorm, UpsamplingNearest
 from .simple_unet import (
     SimpleUNet,
     SimpleUNetBasicBlock,
@@ -14,5 +14,5 @@ from .simple_unet import (
 __all__ = [
     "AvgPool", "BatchNorm", "GroupNorm", "MaxPool", "SimpleUNet", "SimpleUNetBasicBlock", "SimpleUNetBottleneck", "SimpleUNetConvBlock", "SimpleUNetDown",
     "SimpleUNetDownUp", "SimpleUNetPad", "SimpleUNetUnpad", "SimpleUNetUp", "SparseConv3d", "SparseConvTranspose3d", "SyncBatchNorm",
-    "UpsamplingNearest",
+    "UpsamplingNearest", "conv_bn_act",
 ]

@@ -93,7 +93,7 @@ class BatchNorm(nn.BatchNorm1d):
             raise ValueError("activation must be None or 'relu'")
         self.activation, self.process_group = activation, process_group
 
-    def _rows(self, x: torch.Tensor) -> torch.Tensor:
+    def _rows(self, x: torch.Tensor, conv_stats=None) -> torch.Tensor:
         training = self.training or self.running_mean is None
         momentum = 0.0 if self.momentum is None else self.momentum
         if self.training and self.track_running_stats and self.num_batches_tracked is not None:
@@ -108,7 +108,7 @@ class BatchNorm(nn.BatchNorm1d):
                 group = self.process_group if self.process_group is not None else dist.group.WORLD
         return _norm.batch_norm_rows(x, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
                                      self.running_var if self.track_running_stats else None, training, momentum, self.eps,
-                                     relu=self.activation == "relu", group=group)
+                                     relu=self.activation == "relu", group=group, conv_stats=conv_stats)
 
     def forward(self, data: JaggedTensor, grid=None) -> JaggedTensor:  # type: ignore[override]
         with record_function(repr(self)):
@@ -168,6 +168,47 @@ class SyncBatchNorm(BatchNorm):
         for name, child in module.named_children():
             out.add_module(name, cls.convert_sync_batchnorm(child, process_group))
         return out
+
+
+def conv_bn_act(conv: _SparseConv3dBase, norm: BatchNorm, data: JaggedTensor, plan: ConvolutionPlan, residual: "JaggedTensor | None" = None,
+                final_relu: bool = False) -> JaggedTensor:
+    """``norm(conv(data, plan)) + residual`` (then a ReLU if ``final_relu``: the tail of the reference's residual block,
+    fvdb/nn/simple_unet.py:182-188) -- the conv -> BatchNorm -> ReLU block of the reference's networks
+    (fvdb/nn/modules.py:484-521, fvdb/nn/simple_unet.py:233-243) with the passes over ``[N, C]`` folded into the GEMM epilogue:
+
+    * training: the convolution epilogue also writes per-block column sums of its output, BatchNorm takes its batch
+      statistics from them (no statistics pass) and applies normalisation + activation in one streaming pass; gradients
+      flow through the ordinary backward of both modules;
+    * inference (no grad, running statistics): BatchNorm folds into a per-channel scale / shift, and scale, shift, the
+      residual add and the ReLU all run in the convolution kernel's epilogue -- ONE kernel for the whole block.
+
+    Falls back to the separate modules wherever the fused epilogue does not exist (CUDA-core path, K = S = 1 matmul plans)."""
+    name = "SparseConvTranspose3d" if conv._transposed else "SparseConv3d"
+    if not plan.valid_usage(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, transposed=conv._transposed):
+        raise ValueError(f"Convolution plan used with a {name} module that had mismatched input/output channels, kernel size, or stride, or transposition")
+    x = data.jdata
+    relu = norm.activation == "relu"
+    training = norm.training or norm.running_mean is None
+    fusable = plan.fused_epilogue_available(x, conv.weight) and _norm.native_rows_supported(x.new_empty((1, conv.out_channels)).to(torch.result_type(x, conv.weight)))
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in list(conv.parameters()) + list(norm.parameters())))
+    if fusable and not training and not needs_grad:
+        with record_function(f"conv_bn_act[inference]({conv!r})"):
+            inv = torch.rsqrt(norm.running_var.float() + norm.eps)
+            scale = inv * norm.weight.float() if norm.weight is not None else inv
+            shift = (norm.bias.float() if norm.bias is not None else 0.0) - norm.running_mean.float() * scale
+            return plan.execute_inference(data, conv.weight, conv.bias, scale=scale, shift=shift, residual=residual,
+                                          relu=(1 if relu else 0) | (2 if final_relu else 0))
+    if fusable and training and x.shape[0] > 0:
+        with record_function(f"conv_bn_act[train]({conv!r})"):
+            y, stats = plan.execute_with_stats(data, conv.weight, conv.bias)
+            out = y.jagged_like(norm._rows(y.jdata, conv_stats=stats))
+    else:
+        out = norm(conv(data, plan))
+    if residual is not None:
+        out = out.jagged_like(out.jdata + residual.jdata)
+    if final_relu:
+        out = out.jagged_like(torch.relu(out.jdata))
+    return out
 
 
 class _Pool(nn.Module):

@@ -223,8 +223,9 @@ FVC_API size_t fvc_conv_weights_bytes(int32_t cin, int32_t cout, int64_t kernel_
 FVC_API int fvc_conv_prepare_weights(const void *weights, const int64_t strides[5], int32_t dtype_in, int32_t cout, int32_t cin, int32_t k0,
                                      int32_t k1, int32_t k2, int32_t transpose, int32_t flip_taps, int32_t dtype, int32_t path, void *prepared,
                                      size_t prepared_bytes, fvc_stream_t stream);
-/* stored[o,c] = act(((acc[o,c] + bias[c]) * scale[c] + shift[c]) + residual[o,c]); every member may be NULL / 0.
- * bias / residual in `dtype`, scale / shift fp32 (an eval-mode BatchNorm folds into them).  stats: fp32
+/* stored[o,c] = act2(act1((acc[o,c] + bias[c]) * scale[c] + shift[c]) + residual[o,c]); every member may be NULL / 0.
+ * relu bit 0: act1 = ReLU (the block's activation, before a skip connection joins); bit 1: act2 = ReLU (after it:
+ * fvdb/nn/simple_unet.py:187-188).  bias / residual in `dtype`, scale / shift fp32 (an eval-mode BatchNorm folds into them).  stats: fp32
  * [fvc_conv_stats_blocks()][2][Cout], per block of rows_per_block consecutive output rows the column sums and sums of squares
  * of the STORED values (what a BatchNorm statistics pass over y would read) -- written, not accumulated; deterministic.
  * scale / shift / residual / relu / stats need the tensor-core path (FVC_ERR_UNSUPPORTED otherwise). */

@@ -158,10 +158,48 @@ class CoordIndex:
             if float(span[0]) * float(span[1]) * float(span[2]) * float(span[3]) < 2.0**62:
                 self._lo, self._span = lo, span
                 self._packed = self._pack(self._sorted)
+        # Densest case (a few million voxels filling a box, kernel volumes of 125): a dense row table over the bounding
+        # box turns a lookup into one fancy-indexing read.  Only when the box holds at most 2^26 cells.
+        self._dense = None
+        if self._packed is not None and int(np.prod(self._span)) <= 2**26:
+            self._dense = np.full(int(np.prod(self._span)), -1, dtype=np.int32)
+            self._dense[self._packed] = self._rows
 
     def _pack(self, table: np.ndarray) -> np.ndarray:
         rel = table - self._lo
         return ((rel[:, 0] * self._span[1] + rel[:, 1]) * self._span[2] + rel[:, 2]) * self._span[3] + rel[:, 3]
+
+    def prepare(self, bidx: np.ndarray, ijk: np.ndarray):
+        """Base queries for ``lookup_offset``: relative coordinates and packed keys (packed / dense tables only)."""
+        if self._packed is None:
+            return None
+        ijk = np.asarray(ijk, dtype=np.int64).reshape(-1, 3)
+        bidx = np.broadcast_to(np.asarray(bidx, dtype=np.int64).reshape(-1), (ijk.shape[0],))
+        rel = np.concatenate([bidx[:, None], ijk], axis=1) - self._lo
+        ok_b = (rel[:, 0] >= 0) & (rel[:, 0] < self._span[0])
+        key = ((rel[:, 0] * self._span[1] + rel[:, 1]) * self._span[2] + rel[:, 2]) * self._span[3] + rel[:, 3]
+        return rel, ok_b, key
+
+    def lookup_offset(self, prepared, offset) -> np.ndarray:
+        """``lookup(bidx, ijk + offset)`` for queries prepared once: a constant offset moves the packed key by a constant, so
+        a whole stencil costs one bounds test and one table read per tap (same answers as ``lookup``)."""
+        rel, inside, key = prepared
+        inside = inside.copy()
+        for d in range(3):
+            c = rel[:, d + 1] + int(offset[d])
+            inside &= (c >= 0) & (c < self._span[d + 1])
+        delta = (int(offset[0]) * int(self._span[2]) + int(offset[1])) * int(self._span[3]) + int(offset[2])
+        keys = key[inside] + delta
+        out = np.full(rel.shape[0], -1, dtype=np.int64)
+        if self._dense is not None:
+            out[inside] = self._dense[keys]
+            return out
+        pos = np.minimum(np.searchsorted(self._packed, keys), self.n - 1)
+        hit = self._packed[pos] == keys
+        rows = np.full(keys.shape[0], -1, dtype=np.int64)
+        rows[hit] = self._rows[pos[hit]]
+        out[inside] = rows
+        return out
 
     def lookup(self, bidx: np.ndarray, ijk: np.ndarray) -> np.ndarray:
         ijk = np.asarray(ijk, dtype=np.int64).reshape(-1, 3)
@@ -173,6 +211,9 @@ class CoordIndex:
         if self._packed is not None:
             inside = np.all((query >= self._lo) & (query < self._lo + self._span), axis=1)
             keys = self._pack(query[inside])
+            if self._dense is not None:
+                out[inside] = self._dense[keys]
+                return out
             pos = np.minimum(np.searchsorted(self._packed, keys), self.n - 1)
             hit = self._packed[pos] == keys
             rows = np.full(keys.shape[0], -1, dtype=np.int64)
@@ -253,8 +294,15 @@ def build_topology(feat_ijk, feat_bidx, out_ijk, out_bidx, kernel_size, stride, 
     out_bidx_ = np.asarray(out_bidx, dtype=np.int64).reshape(-1)
     index = CoordIndex(feat_ijk, feat_bidx)
     per_tap = []
+    # forward probes are fineFromCoarse(out, tap) = (S * out - pad) + tap: one prepared base query, a constant offset per tap
+    prepared = None if (transposed or n_out == 0 or n_feat == 0) else index.prepare(out_bidx_, geometry.fine_from_coarse(out_ijk_, (0, 0, 0)))
     for k in range(K):
         tap = geometry.tap_coord(k)
+        if prepared is not None:
+            rows = index.lookup_offset(prepared, tap)
+            out_rows = np.nonzero(rows >= 0)[0]
+            per_tap.append((rows[out_rows].astype(np.int32), out_rows.astype(np.int32)))
+            continue
         if transposed:  # :129-141
             probe, ok = geometry.coarse_from_fine(out_ijk_, tap)
             rows = index.lookup(out_bidx_, probe)

@@ -170,6 +170,49 @@ def test_wgrad_allreduce_world_size_2_gloo(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+def _syncbn_worker(rank, world, port, out_dir):
+    import os
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fvdb
+
+    torch.manual_seed(3)
+    rows = torch.randn(300, 12, dtype=torch.float64) * 3 + 50  # |mean| >> std
+    # rank 1 owns ZERO rows (fewer grids than ranks under the by-grid partition): it must still join every collective
+    mine = rows if rank == 0 else rows[:0]
+    bn = fvdb.nn.SyncBatchNorm(12, activation="relu").double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5), bn.bias.uniform_(-0.5, 0.5)
+    x = mine.clone().requires_grad_()
+    jt = fvdb.JaggedTensor.from_data_and_indices(x, torch.zeros(len(mine), dtype=torch.int32), 1)
+    y = bn(jt).jdata
+    loss = y.square().sum()
+    loss.backward()
+    ref = torch.nn.BatchNorm1d(12).double()
+    ref.load_state_dict({k: v.clone() for k, v in bn.state_dict().items() if k in ("weight", "bias")}, strict=False)
+    xr = rows.clone().requires_grad_()
+    yr = torch.relu(ref(xr))
+    yr.square().sum().backward()
+    if rank == 0:
+        torch.testing.assert_close(y, yr, rtol=1e-9, atol=1e-9)
+        torch.testing.assert_close(x.grad, xr.grad, rtol=1e-8, atol=1e-8)
+        torch.testing.assert_close(bn.running_var, ref.running_var, rtol=1e-9, atol=1e-9)
+    else:
+        assert y.shape == (0, 12) and x.grad.shape == (0, 12)
+    dist.barrier()
+    dist.destroy_process_group()
+    Path(out_dir, f"bn{rank}").write_text("ok")
+
+
+def test_sync_batch_norm_with_an_empty_rank_world_size_2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_syncbn_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "bn0").exists() and (tmp_path / "bn1").exists()
+
+
 def test_group_norm_matches_per_grid_torch_group_norm():
     # fvdb.nn.GroupNorm == torch GroupNorm applied to each grid's [1, C, N_b] slab (reference modules.py:452-480); pure torch
     # composition, so it runs on the CPU with a stand-in for the grid.
