@@ -918,6 +918,7 @@ def main():
     ap.add_argument("--unfused-bn", action="store_true", help="c3: fvdb.nn.BatchNorm as a separate module call (statistics pass + apply pass) instead of the conv-epilogue statistics")
     ap.add_argument("--sync-bn", action="store_true", help="c3: batch statistics over all ranks (fvdb.nn.SyncBatchNorm)")
     ap.add_argument("--grids", type=int, default=0, help="override the number of grids per GPU (experiments)")
+    ap.add_argument("--variant", type=int, default=0, help="experiments: pipeline-shape variant of the tensor-core forward kernel (fvc_set_tuning)")
     ap.add_argument("--c4-grids", type=int, default=0, help="override the number of grids of the strong_c4 sub-record (experiments)")
     args = ap.parse_args()
     config_name = args.config or "c2"
@@ -925,6 +926,10 @@ def main():
     cfg = dict(CONFIGS[config_name])
     if args.grids:
         cfg["grids"] = args.grids
+    if args.variant and args.impl == "ours":
+        from fvdb import _fvdb_cpp
+
+        _fvdb_cpp.set_kernel_variant(args.variant)
     if args.impl == "reference":
         run_reference(args, cfg)
     elif config_name == "c3":

@@ -43,6 +43,13 @@ static int run_forward(const void *x, const void *w, bool w_prepared, bool x_spl
 
 extern "C" {
 
+int32_t fvc_conv_kernel_family(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, int32_t pass) {
+    if (path == 1)
+        return 1;
+    const bool tc = pass == 0 ? tc_forward_supported(cin, cout, kernel_volume, dtype) : tc_wgrad_supported(cin, cout, kernel_volume, dtype);
+    return tc ? 2 : 1;
+}
+
 int fvc_set_tuning(int32_t key, int32_t value) {
     FVC_REQUIRE(key == 0, FVC_ERR_VALUE, "unknown tuning key %d", key);
     g_tc_variant = value;
@@ -147,15 +154,16 @@ int fvc_conv_wgrad_ex(const void *x, int32_t x_is_split, const void *dy, int32_t
     if (out_bytes == 0)
         return FVC_OK;
     FVC_REQUIRE(grad_w, FVC_ERR_RUNTIME, "fvc_conv_wgrad: null grad_w pointer");
-    FVC_REQUIRE(offsets_host, FVC_ERR_RUNTIME, "fvc_conv_wgrad: offsets_host must be provided");
-    if (n_out == 0 || n_in == 0 || offsets_host[kernel_volume] == 0) { // GatherScatterDefault.cu:771-777
+    const bool tc_ok = nbr && tc_wgrad_supported(cin, cout, kernel_volume, dtype);
+    const bool run_tc = tc_ok && path != 1;
+    FVC_REQUIRE(offsets_host || run_tc, FVC_ERR_RUNTIME, "fvc_conv_wgrad: offsets_host must be provided");
+    if (n_out == 0 || n_in == 0 || (offsets_host && offsets_host[kernel_volume] == 0)) { // GatherScatterDefault.cu:771-777
         FVC_CUDA(cudaMemsetAsync(grad_w, 0, out_bytes, stream));
         return FVC_OK;
     }
-    FVC_REQUIRE(gather && scatter && offsets_dev, FVC_ERR_RUNTIME, "fvc_conv_wgrad: null CSR pointer");
+    FVC_REQUIRE(run_tc || (gather && scatter && offsets_dev), FVC_ERR_RUNTIME, "fvc_conv_wgrad: null CSR pointer");
     WgradArgs a{x, dy, gather, scatter, offsets_host, offsets_dev, nbr, pitch, tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype,
                 grad_w, scratch, scratch_bytes, stream, x_is_split != 0, dy_is_split != 0};
-    const bool tc_ok = nbr && tc_wgrad_supported(cin, cout, kernel_volume, dtype);
     if (path == 2 && !tc_ok)
         return set_error(FVC_ERR_UNSUPPORTED, "tensor-core wgrad does not admit dtype code %d with channels %d -> %d", dtype, cin, cout);
     if (tc_ok && path != 1)

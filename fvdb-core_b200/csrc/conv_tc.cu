@@ -82,7 +82,8 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     // Three small CTAs per SM beat two larger ones by ~10 % on the 32- and 64-channel shapes: more independent
     // producer -> MMA -> commit chains hide the per-unit hand-off latency (profiles/r01_experiments.md)
     static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = int(233472 / (SMEM + 1024 + 768));
-    static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > 3 ? 3 : BY_TMEM) : (BY_SMEM > 3 ? 3 : BY_SMEM);
+    static constexpr int CTA_CAP = MODE == 1 ? 4 : 3;
+    static constexpr int CTAS_PER_SM = BY_TMEM < BY_SMEM ? (BY_TMEM > CTA_CAP ? CTA_CAP : BY_TMEM) : (BY_SMEM > CTA_CAP ? CTA_CAP : BY_SMEM);
     static_assert(CTAS_PER_SM >= 1, "configuration does not fit one SM");
     static_assert((CIN % 64 == 0 || CIN == 32 || CIN == 16) && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * ACC_COLS <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
@@ -797,7 +798,7 @@ static inline TcShape tc_shape(int32_t cin, int32_t cout, bool split) {
     case 16: return wide ? TcShape{8, 4, 2, 4, 1} : TcShape{8, 3, 2, 4, 0};
     case 32: return wide ? TcShape{4, 4, 2, 4, 1} : TcShape{4, 3, 2, 4, 0};
     case 64: return wide ? TcShape{2, 3, 2, 3, 1} : TcShape{2, 3, 2, 4, 0};
-    case 128: return wide ? TcShape{1, 3, 2, 3, 1} : TcShape{1, 2, 2, 4, 0};
+    case 128: return wide ? TcShape{2, 4, 2, 3, 1} : TcShape{1, 2, 2, 4, 0};
     default: return wide ? TcShape{2, 4, 2, 4, 1} : TcShape{2, 6, 3, 4, 0};
     }
 }
@@ -871,15 +872,34 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
     if (g_tc_variant != 0 && a.cin == a.cout && (a.cin == 64 || a.cin == 128)) {
         const bool c64 = a.cin == 64;
         switch (g_tc_variant) {
-        case 1: return c64 ? launch_tc_fwd<64, 64, 2, 3, 2, 4, false, 0>(a, x, img) : launch_tc_fwd<128, 128, 1, 2, 2, 4, false, 0>(a, x, img); // round-1 kernel
         case 2: return c64 ? launch_tc_fwd<64, 64, 4, 4, 2, 4, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 4, 2, 4, false, 1>(a, x, img); // 2 CTAs / SM
         case 3: return c64 ? launch_tc_fwd<64, 64, 8, 8, 3, 4, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 4, 8, 2, 4, false, 1>(a, x, img); // 1 CTA / SM
         case 4: return c64 ? launch_tc_fwd<64, 64, 2, 4, 2, 4, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 4, 2, 4, false, 1>(a, x, img);
         case 5: return c64 ? launch_tc_fwd<64, 64, 2, 4, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 4, 2, 2, false, 1>(a, x, img);
         case 6: return c64 ? launch_tc_fwd<64, 64, 4, 5, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 4, 2, 3, false, 1>(a, x, img);
+        case 7: return c64 ? launch_tc_fwd<64, 64, 2, 2, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 2, 1, 2, false, 1>(a, x, img); // 4 CTAs / SM
+        case 8: return c64 ? launch_tc_fwd<64, 64, 1, 2, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 3, 2, 2, false, 1>(a, x, img);
+        case 9: return c64 ? launch_tc_fwd<64, 64, 2, 3, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 4, 6, 2, 3, false, 1>(a, x, img);
+        case 10: return c64 ? launch_tc_fwd<64, 64, 4, 3, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 3, 2, 3, false, 1>(a, x, img);
         default: break;
         }
     }
+#define FVC_TC_LEGACY(CI, CO, T, S, B) \
+    if (a.cin == CI && a.cout == CO)  \
+        return launch_tc_fwd<CI, CO, T, S, B, 4, false, 0>(a, x, img);
+#define FVC_TC_LEGACY_CIN(CI)     \
+    FVC_TC_LEGACY(CI, 16, 8, 3, 2)  \
+    FVC_TC_LEGACY(CI, 32, 4, 3, 2)  \
+    FVC_TC_LEGACY(CI, 64, 2, 3, 2)  \
+    FVC_TC_LEGACY(CI, 128, 1, 2, 2) \
+    FVC_TC_LEGACY(CI, 256, 2, 6, 3)
+    if (g_tc_variant == 1) { // the round-1 kernel (four producer warps share every unit, map ring) for every wide shape: A/B baseline
+        FVC_TC_LEGACY_CIN(64)
+        FVC_TC_LEGACY_CIN(128)
+        FVC_TC_LEGACY_CIN(256)
+    }
+#undef FVC_TC_LEGACY_CIN
+#undef FVC_TC_LEGACY
 #define FVC_TC_NARROW(CI)                      \
     FVC_TC_LAUNCH(CI, 16, 8, 3, 2, 4, false, 0) \
     FVC_TC_LAUNCH(CI, 32, 4, 3, 2, 4, false, 0) \
@@ -890,7 +910,7 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
     FVC_TC_LAUNCH(CI, 16, 8, 4, 2, 4, false, 1) \
     FVC_TC_LAUNCH(CI, 32, 4, 4, 2, 4, false, 1) \
     FVC_TC_LAUNCH(CI, 64, 2, 3, 2, 3, false, 1) \
-    FVC_TC_LAUNCH(CI, 128, 1, 3, 2, 3, false, 1) \
+    FVC_TC_LAUNCH(CI, 128, 2, 4, 2, 3, false, 1) \
     FVC_TC_LAUNCH(CI, 256, 2, 4, 2, 4, false, 1)
     FVC_TC_NARROW(16)
     FVC_TC_NARROW(32)

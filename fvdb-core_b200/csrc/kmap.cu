@@ -52,7 +52,7 @@ __device__ __forceinline__ LeafBox probe_box(const Geometry &g, const int origin
 // 16-byte loads, then every lane keeps one output voxel in registers and answers its K^3 probes from shared memory.
 __global__ void __launch_bounds__(KM_THREADS)
 kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transposed, int32_t *__restrict__ nbr,
-                  int64_t pitch, unsigned long long *__restrict__ tap_counts) {
+                  int64_t pitch, unsigned long long *__restrict__ tap_counts, unsigned long long *__restrict__ tile_mask, int mask_words) {
     __shared__ __align__(16) uint64_t s_mask[KM_WARPS][KM_MAX_NB][8];
     __shared__ __align__(16) uint16_t s_prefix[KM_WARPS][KM_MAX_NB][8];
     __shared__ int s_base[KM_WARPS][KM_MAX_NB];
@@ -127,6 +127,11 @@ kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transpose
 #pragma unroll
             for (int d = 0; d < 3; ++d)
                 c[d] = transposed ? c[d] + g.pad[d] : g.s[d] * c[d] - g.pad[d];
+            // tile tap-mask, fused (it used to be a second pass over the whole map): the 32 rows of this chunk lie in at most two
+            // 128-row tiles; the taps that hit are collected per tile in registers and OR-ed into the mask once per 64 taps
+            const int64_t tile_lo = (int64_t(base) + j0) >> 7;
+            const unsigned in_lo = __ballot_sync(0xffffffffu, ((int64_t(base) + j) >> 7) == tile_lo);
+            unsigned long long taps_lo = 0ull, taps_hi = 0ull;
             for (int k = 0; k < k3; ++k) {
                 int t[3];
                 if (small_taps) {
@@ -174,6 +179,17 @@ kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transpose
                         atomicAdd(&s_cnt[k], uint32_t(__popc(hits)));
                     else
                         atomicAdd(tap_counts + k, (unsigned long long)__popc(hits));
+                }
+                if (tile_mask) {
+                    taps_lo |= (unsigned long long)((hits & in_lo) != 0u) << (k & 63);
+                    taps_hi |= (unsigned long long)((hits & ~in_lo) != 0u) << (k & 63);
+                    if ((k & 63) == 63 || k == k3 - 1) {
+                        if (lane == 0 && taps_lo)
+                            atomicOr(tile_mask + tile_lo * mask_words + (k >> 6), taps_lo);
+                        if (lane == 0 && taps_hi)
+                            atomicOr(tile_mask + (tile_lo + 1) * mask_words + (k >> 6), taps_hi);
+                        taps_lo = taps_hi = 0ull;
+                    }
                 }
             }
         }
@@ -256,6 +272,19 @@ __global__ void reverse_dense_kernel(const int32_t *__restrict__ gather, const i
                 hi = mid;
         }
         nbr_rev[int64_t(lo) * pitch_rev + gather[p]] = scatter[p];
+    }
+}
+
+// nbr_rev[k][i] = o for every (k, o) with nbr[k][o] = i >= 0: the input-stationary map straight from the output-stationary
+// one (no CSR detour); a feature row is reached through tap k by at most one output row, so there is no write conflict
+__global__ void reverse_from_dense_kernel(const int32_t *__restrict__ nbr, int64_t pitch, int64_t n_out, int k3,
+                                          int32_t *__restrict__ nbr_rev, int64_t pitch_rev) {
+    const int64_t total = int64_t(k3) * n_out;
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t k = e / n_out, o = e - k * n_out;
+        const int32_t i = __ldg(nbr + k * pitch + o);
+        if (i >= 0)
+            nbr_rev[k * pitch_rev + i] = int32_t(o);
     }
 }
 
@@ -423,7 +452,7 @@ using namespace fvc;
 extern "C" {
 
 int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_grid, const int32_t kernel_size[3],
-                   const int32_t stride[3], int32_t transposed, int32_t *nbr, int64_t pitch, int64_t *tap_counts,
+                   const int32_t stride[3], int32_t transposed, int32_t *nbr, int64_t pitch, int64_t *tap_counts, uint64_t *tile_mask,
                    fvc_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     FVC_REQUIRE(feature_grid && output_grid, FVC_ERR_RUNTIME, "feature_grid and output_grid must be provided");
@@ -444,10 +473,16 @@ int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_
     FVC_REQUIRE(pitch >= output_grid->total_voxels, FVC_ERR_RUNTIME, "map pitch %lld < output voxels %lld",
                 (long long)pitch, (long long)output_grid->total_voxels);
     FVC_CUDA(cudaMemsetAsync(tap_counts, 0, size_t(g.volume) * 8, stream));
+    const int mask_words = int((g.volume + 63) / 64);
+    if (tile_mask) {
+        FVC_REQUIRE(g.volume <= 4096, FVC_ERR_UNSUPPORTED, "kernel volume %lld exceeds the tile-mask limit 4096", (long long)g.volume);
+        FVC_CUDA(cudaMemsetAsync(tile_mask, 0, size_t(ceil_div(output_grid->total_voxels, 128)) * mask_words * 8, stream));
+    }
     if (output_grid->num_leaves == 0)
         return FVC_OK;
     kmap_build_kernel<<<unsigned(ceil_div(output_grid->num_leaves, KM_WARPS)), KM_THREADS, 0, stream>>>(
-        *feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, reinterpret_cast<unsigned long long *>(tap_counts));
+        *feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, reinterpret_cast<unsigned long long *>(tap_counts),
+        reinterpret_cast<unsigned long long *>(tile_mask), mask_words);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }
@@ -506,6 +541,20 @@ int fvc_kmap_reverse_dense(const int32_t *gather, const int32_t *scatter, const 
         return FVC_OK;
     reverse_dense_kernel<<<grid_for(total_pairs, 256), 256, 0, stream>>>(gather, scatter, offsets_dev, int(kernel_volume),
                                                                          total_pairs, nbr_rev, pitch_rev);
+    FVC_LAUNCH_CHECK();
+    return FVC_OK;
+}
+
+int fvc_kmap_reverse_from_dense(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, int64_t n_feature, int32_t *nbr_rev,
+                                int64_t pitch_rev, fvc_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    FVC_REQUIRE(pitch_rev >= n_feature && pitch >= n_out, FVC_ERR_RUNTIME, "map pitch smaller than the row count");
+    if (kernel_volume == 0 || pitch_rev == 0)
+        return FVC_OK;
+    FVC_CUDA(cudaMemsetAsync(nbr_rev, 0xFF, size_t(kernel_volume) * size_t(pitch_rev) * 4, stream));
+    if (n_out == 0)
+        return FVC_OK;
+    reverse_from_dense_kernel<<<grid_for(kernel_volume * n_out, 256), 256, 0, stream>>>(nbr, pitch, n_out, int(kernel_volume), nbr_rev, pitch_rev);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }

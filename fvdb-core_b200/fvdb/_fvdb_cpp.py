@@ -314,21 +314,69 @@ def _tile_mask(nbr: torch.Tensor, rows: int, kernel_volume: int) -> "torch.Tenso
 class _MapCore:
     """Storage shared by a topology and its constant-time reversed view.
 
-    ``nbr`` is the output-stationary tap-major dense map of the *built* direction ([K^3, pitch] int32,
-    feature row or -1); ``nbr_rev`` (input-stationary, built lazily from the CSR pairs) serves dgrad of
-    the built direction and the forward pass of the reversed view.
+    ``nbr`` is the output-stationary tap-major dense map of the *built* direction ([K^3, pitch] int32, feature row or -1) and
+    ``mask`` its per-tile tap bitmask, both written by ONE kernel with no host synchronisation.  Everything else is derived
+    lazily, on first use: ``nbr_rev`` (input-stationary; serves dgrad of the built direction and the forward pass of the
+    reversed view), the host offsets (the one D2H read of the tap counts, reference: GatherScatterDefault.cu:149) and the
+    reference's CSR-by-tap arrays -- the tensor-core executors read only the dense maps, so a training step never builds them.
     """
 
-    def __init__(self, gather, scatter, offsets_host, offsets_dev, nbr, n_feature, n_output, kernel_volume, symmetric=False):
+    def __init__(self, nbr, mask, tap_counts, n_feature, n_output, kernel_volume, symmetric=False):
         # symmetric: same grid on both sides, stride 1, odd kernel -> nbr_rev[k] == nbr[K^3 - 1 - k] (row i reaches o through tap k
         # iff o reaches i through the mirrored tap), so dgrad can run on `nbr` itself with the taps of W mirrored
         self.symmetric = bool(symmetric)
-        self.gather, self.scatter = gather, scatter
-        self.offsets_host, self.offsets_dev = offsets_host, offsets_dev
-        self.nbr, self._nbr_rev, self._mask_rev = nbr, None, None
+        self.nbr, self.mask, self._tap_counts = nbr, mask, tap_counts
+        self._nbr_rev, self._mask_rev = None, None
+        self._offsets_host, self._offsets_dev, self._gather, self._scatter = None, None, None, None
         self.n_feature, self.n_output, self.kernel_volume = n_feature, n_output, kernel_volume
-        self.mask = _tile_mask(nbr, n_output, kernel_volume)
-        self.total_pairs = int(offsets_host[-1]) if offsets_host.numel() else 0
+
+    # ---- lazily derived views ---------------------------------------------------------------------
+    @property
+    def offsets_host(self) -> torch.Tensor:
+        if self._offsets_host is None:
+            offsets = torch.zeros(self.kernel_volume + 1, dtype=torch.int64)
+            offsets[1:] = torch.cumsum(self._tap_counts.cpu(), 0)  # the one D2H read (synchronises), only when somebody asks
+            self._offsets_host = offsets
+        return self._offsets_host
+
+    @property
+    def total_pairs(self) -> int:
+        return int(self.offsets_host[-1]) if self.kernel_volume else 0
+
+    def _csr(self) -> None:
+        if self._gather is not None:
+            return
+        device, k3, n_out = self.nbr.device, self.kernel_volume, self.n_output
+        total = self.total_pairs
+        with torch.cuda.device(device):
+            stream = _stream(device)
+            gather = torch.empty(total, dtype=torch.int32, device=device)
+            scatter = torch.empty(total, dtype=torch.int32, device=device)
+            offsets_dev = torch.empty(k3 + 1, dtype=torch.int64, device=device)
+            scratch_bytes = int(lib.fvc_kmap_csr_scratch_bytes(n_out, k3))
+            scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device)
+            check(
+                lib.fvc_kmap_to_csr(
+                    _ptr(self.nbr), int(self.nbr.shape[1]), n_out, k3, self._tap_counts.data_ptr(), offsets_dev.data_ptr(), _ptr(gather), _ptr(scatter),
+                    scratch.data_ptr(), scratch_bytes, stream,
+                )
+            )
+        self._gather, self._scatter, self._offsets_dev = gather, scatter, offsets_dev
+
+    @property
+    def gather(self) -> torch.Tensor:
+        self._csr()
+        return self._gather
+
+    @property
+    def scatter(self) -> torch.Tensor:
+        self._csr()
+        return self._scatter
+
+    @property
+    def offsets_dev(self) -> torch.Tensor:
+        self._csr()
+        return self._offsets_dev
 
     def nbr_rev(self) -> torch.Tensor:
         if self._nbr_rev is None:
@@ -337,9 +385,8 @@ class _MapCore:
             rev = torch.empty((self.kernel_volume, pitch), dtype=torch.int32, device=device)
             with torch.cuda.device(device):
                 check(
-                    lib.fvc_kmap_reverse_dense(
-                        _ptr(self.gather), _ptr(self.scatter), self.offsets_dev.data_ptr(), self.kernel_volume, self.total_pairs,
-                        self.n_feature, _ptr(rev), pitch, _stream(device),
+                    lib.fvc_kmap_reverse_from_dense(
+                        _ptr(self.nbr), int(self.nbr.shape[1]), self.n_output, self.kernel_volume, self.n_feature, _ptr(rev), pitch, _stream(device)
                     )
                 )
             self._nbr_rev = rev
@@ -349,6 +396,15 @@ class _MapCore:
     def mask_rev(self) -> "torch.Tensor | None":
         self.nbr_rev()
         return self._mask_rev
+
+    def zero_degree_outputs(self) -> int:
+        """Output rows no tap reaches (coverage policy, reference convolution_plan.py:341-345), from the dense map."""
+        if self.n_output == 0:
+            return 0
+        degree = torch.empty(self.n_output, dtype=torch.int32, device=self.nbr.device)
+        with torch.cuda.device(self.nbr.device):
+            check(lib.fvc_kmap_degree(_ptr(self.nbr), int(self.nbr.shape[1]), self.n_output, self.kernel_volume, degree.data_ptr(), _stream(self.nbr.device)))
+        return int((degree == 0).sum())
 
 
 class GatherScatterDefaultTopology:
@@ -360,7 +416,7 @@ class GatherScatterDefaultTopology:
 
     gather_indices = property(lambda self: self._core.scatter if self._reversed else self._core.gather)
     scatter_indices = property(lambda self: self._core.gather if self._reversed else self._core.scatter)
-    offsets = property(lambda self: self._core.offsets_host)
+    offsets = property(lambda self: self._core.offsets_host)  # int64 [K^3 + 1] on the HOST, as in the reference (GatherScatterDefault.h:70)
     feature_total_voxels = property(lambda self: self._core.n_output if self._reversed else self._core.n_feature)
     output_total_voxels = property(lambda self: self._core.n_feature if self._reversed else self._core.n_output)
     kernel_volume = property(lambda self: self._core.kernel_volume)
@@ -407,22 +463,13 @@ def _build_topology(feature_grid: GridBatchData, output_grid: GridBatchData, ker
         stream = _stream(device)
         nbr = torch.empty((k3, pitch), dtype=torch.int32, device=device)
         tap_counts = torch.empty(k3, dtype=torch.int64, device=device)
-        check(lib.fvc_kmap_build(feature_grid.struct, output_grid.struct, i3(ks), i3(st), int(transposed), _ptr(nbr), pitch, tap_counts.data_ptr(), stream))
-        offsets_host = torch.zeros(k3 + 1, dtype=torch.int64)
-        offsets_host[1:] = torch.cumsum(tap_counts.cpu(), 0)  # the one D2H sync of the build (reference: GatherScatterDefault.cu:149)
-        total = int(offsets_host[-1])
-        gather = torch.empty(total, dtype=torch.int32, device=device)
-        scatter = torch.empty(total, dtype=torch.int32, device=device)
-        offsets_dev = torch.empty(k3 + 1, dtype=torch.int64, device=device)
-        scratch_bytes = int(lib.fvc_kmap_csr_scratch_bytes(n_out, k3))
-        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device)
-        check(
-            lib.fvc_kmap_to_csr(
-                _ptr(nbr), pitch, n_out, k3, tap_counts.data_ptr(), offsets_dev.data_ptr(), _ptr(gather), _ptr(scatter), scratch.data_ptr(), scratch_bytes, stream
-            )
-        )
+        mask = None
+        if n_out > 0 and 0 < k3 <= 4096:  # the tile tap-mask comes out of the same kernel
+            mask = torch.empty(((n_out + 127) // 128) * ((k3 + 63) // 64), dtype=torch.int64, device=device)
+        # ONE kernel, no host synchronisation: dense map + per-tap pair counts + tile tap-masks
+        check(lib.fvc_kmap_build(feature_grid.struct, output_grid.struct, i3(ks), i3(st), int(transposed), _ptr(nbr), pitch, tap_counts.data_ptr(), _ptr(mask), stream))
     symmetric = feature_grid.is_same(output_grid) and st == [1, 1, 1] and all(k % 2 == 1 for k in ks)
-    core = _MapCore(gather, scatter, offsets_host, offsets_dev, nbr, n_feat, n_out, k3, symmetric=symmetric)
+    core = _MapCore(nbr, mask, tap_counts, n_feat, n_out, k3, symmetric=symmetric)
     return GatherScatterDefaultTopology(core, ks, st, transposed, reversed_view=False)
 
 
@@ -439,6 +486,93 @@ def gs_build_transpose_topology(feature_grid, output_grid, kernel_size, stride) 
 def gs_reverse_topology(topology: GatherScatterDefaultTopology) -> GatherScatterDefaultTopology:
     """Constant-time reversed view aliasing the same tensors (GatherScatterDefault.cu:273-294)."""
     return GatherScatterDefaultTopology(topology._core, topology._kernel_size, topology._stride, not topology._is_transposed, not topology._reversed)
+
+
+def validate_gather_scatter_default_topology(fine_grid: GridBatchData, coarse_grid: GridBatchData, topology, *, gather_indices=None, scatter_indices=None,
+                                             offsets=None, feature_total_voxels=None, output_total_voxels=None) -> None:
+    """Explicit test / debug validation of a kernel map (validateGatherScatterDefaultTopology, GatherScatterDefault.cu:342-527):
+    metadata, offsets, index ranges, every stored edge against the canonical relation ``fine = S * coarse + tap - pad``
+    inside one batch item, no duplicate edge, and stored edge set == complete canonical relation.  Raises RuntimeError with
+    the reference's messages.  The keyword overrides stand in for the corrupted copies the reference test builds
+    (src/tests/GatherScatterDefaultConvTest.cu:876-930).  Runs as torch ops + the native lookup kernel on the grids' device."""
+    if fine_grid.device != coarse_grid.device:
+        raise RuntimeError(f"fine_grid and coarse_grid must be on the same device, got {fine_grid.device} and {coarse_grid.device}")
+    if fine_grid.num_grids != coarse_grid.num_grids:
+        raise RuntimeError(f"fine_grid and coarse_grid batch sizes must match, got {fine_grid.num_grids} and {coarse_grid.num_grids}")
+    forward = not topology.is_transposed
+    feature_grid, output_grid = (fine_grid, coarse_grid) if forward else (coarse_grid, fine_grid)
+    n_feat = topology.feature_total_voxels if feature_total_voxels is None else feature_total_voxels
+    n_out = topology.output_total_voxels if output_total_voxels is None else output_total_voxels
+    if n_feat != feature_grid.total_voxels:
+        raise RuntimeError(f"topology feature voxel count {n_feat} does not match its {'fine' if forward else 'coarse'} domain count {feature_grid.total_voxels}")
+    if n_out != output_grid.total_voxels:
+        raise RuntimeError(f"topology output voxel count {n_out} does not match its {'coarse' if forward else 'fine'} domain count {output_grid.total_voxels}")
+    geometry = ConvolutionGeometry(topology.kernel_size, topology.stride)
+    k3 = topology.kernel_volume
+    if k3 != geometry.kernel_volume:
+        raise RuntimeError(f"topology kernel volume {k3} does not match geometry volume {geometry.kernel_volume}")
+    gather = topology.gather_indices if gather_indices is None else gather_indices
+    scatter = topology.scatter_indices if scatter_indices is None else scatter_indices
+    offs = topology.offsets if offsets is None else offsets
+    total = topology.total_pairs
+    for tensor, name in ((gather, "gather_indices"), (scatter, "scatter_indices")):
+        if tensor.dim() != 1:
+            raise RuntimeError(f"{name} must be one-dimensional")
+        if tensor.dtype != torch.int32:
+            raise RuntimeError(f"{name} must have int32 dtype")
+        if tensor.device != fine_grid.device:
+            raise RuntimeError(f"{name} must be on grid device {fine_grid.device}, got {tensor.device}")
+        if not tensor.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous")
+        if tensor.numel() != total:
+            raise RuntimeError(f"{name} length {tensor.numel()} does not match total pair count {total}")
+    if offs.dim() != 1 or offs.dtype != torch.int64 or offs.device.type != "cpu" or not offs.is_contiguous():
+        raise RuntimeError("offsets must be a contiguous one-dimensional int64 tensor stored on CPU")
+    if offs.numel() != k3 + 1:
+        raise RuntimeError(f"offset length {offs.numel()} does not match kernel volume + 1 ({k3 + 1})")
+    o = offs.tolist()
+    if o[0] != 0:
+        raise RuntimeError(f"offsets must start at zero, got {o[0]}")
+    for tap in range(k3):
+        if o[tap] > o[tap + 1]:
+            raise RuntimeError(f"offsets must be monotone at tap {tap}: {o[tap]} > {o[tap + 1]}")
+    if o[k3] != total:
+        raise RuntimeError(f"final offset {o[k3]} does not match total pair count {total}")
+    g64, s64 = gather.long(), scatter.long()
+    for idx, name, limit in ((g64, "gather", n_feat), (s64, "scatter", n_out)):
+        bad = ((idx < 0) | (idx >= limit)).nonzero()
+        if bad.numel():
+            pair = int(bad[0])
+            raise RuntimeError(f"{name} index out of range at pair {pair}: {int(idx[pair])}")
+    device = fine_grid.device
+    fine_idx, coarse_idx = (g64, s64) if forward else (s64, g64)
+    tap_of_pair = torch.repeat_interleave(torch.arange(k3, device=device), torch.tensor([o[t + 1] - o[t] for t in range(k3)], device=device)) if total else g64
+    ks, st, pad = geometry.kernel_size, geometry.stride, geometry.padding_before
+    taps = torch.tensor([geometry.tap_coord(t) for t in range(k3)], dtype=torch.int32, device=device).reshape(k3, 3)
+    scale, shift = torch.tensor(st, dtype=torch.int32, device=device), torch.tensor(pad, dtype=torch.int32, device=device)
+    if total:
+        crossing = (fine_grid.jidx.long()[fine_idx] != coarse_grid.jidx.long()[coarse_idx]).nonzero()
+        if crossing.numel():
+            raise RuntimeError(f"edge crosses batch domains at pair {int(crossing[0])}")
+        want_fine = coarse_grid.ijk[coarse_idx] * scale + taps[tap_of_pair] - shift  # fineFromCoarse (ConvolutionGeometry.h:99-104)
+        wrong = (fine_grid.ijk[fine_idx] != want_fine).any(dim=1).nonzero()
+        if wrong.numel():
+            pair = int(wrong[0])
+            raise RuntimeError(f"edge does not satisfy canonical fine/coarse geometry at pair {pair}, tap {int(tap_of_pair[pair])}")
+        key = (tap_of_pair * max(n_feat, 1) + (g64 if forward else s64)) * max(n_out, 1) + (s64 if forward else g64)
+        uniq, counts = torch.unique(key, return_counts=True)
+        if uniq.numel() != total:
+            raise RuntimeError("duplicate fine/coarse/tap edge in the stored topology")
+    # the complete canonical relation: every coarse voxel probes every tap on the fine grid (same batch item)
+    expected = 0
+    nc = coarse_grid.total_voxels
+    if nc and k3 and fine_grid.total_voxels:
+        for tap in range(k3):
+            probe = coarse_grid.ijk * scale + taps[tap] - shift
+            hit = ijk_to_index(fine_grid, probe, coarse_grid.jidx, cumulative=True)
+            expected += int((hit >= 0).sum())
+    if expected != total:
+        raise RuntimeError(f"stored topology edge set does not equal the complete canonical relation: got {total} edges, expected {expected}")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -520,7 +654,7 @@ def split_rows(x: torch.Tensor) -> torch.Tensor:
 
 
 def _tensor_core_fp32(cin: int, cout: int, k3: int) -> bool:
-    return _path != 1 and int(lib.fvc_conv_scratch_bytes(1, 1, cin, cout, k3, _lib.FVC_F32)) > 0
+    return int(lib.fvc_conv_kernel_family(cin, cout, k3, _lib.FVC_F32, _path, 0)) == 2
 
 
 class ConvStats:
@@ -613,29 +747,45 @@ def _backward(grad_output, features, weights, topo, name, want_transposed, on_gr
         # wgrad first: dW[k] = X[g]^T . dY[s]  (GatherScatterDefault.cu:806-813).  Its result is the only thing a data-parallel
         # job exchanges, so `on_grad_weights` (e.g. an asynchronous NCCL all-reduce) can overlap the dgrad kernel below.
         grad_weights = torch.empty(tuple(weights.shape), dtype=working, device=device)
-        offsets_host = topo.offsets
         out_map = topo._out_map()
+        # the tensor-core weight gradient reads the dense map only: neither the host offsets (a D2H sync) nor the CSR arrays are
+        # ever materialised on that path
+        tc_wgrad = k3 > 0 and int(lib.fvc_conv_kernel_family(cin, cout, k3, code, _path, 1)) == 2
+        empty = n_feat == 0 or n_out == 0 or k3 == 0 or (not tc_wgrad and topo.total_pairs == 0)
         # fp32 on the tensor pipe: X (kept from the forward call when the caller has it) and dY are split ONCE each and the
         # split rows feed both the weight gradient and dgrad
-        tc32 = working == torch.float32 and n_feat > 0 and n_out > 0 and topo.total_pairs > 0 and _tensor_core_fp32(cin, cout, k3) and _tensor_core_fp32(cout, cin, k3)
+        tc32 = working == torch.float32 and not empty and tc_wgrad and _tensor_core_fp32(cin, cout, k3) and _tensor_core_fp32(cout, cin, k3)
         x_op, x_split = (features_split, 1) if (tc32 and features_split is not None) else (features, 0)
         dy_op, dy_split = (split_rows(grad_output), 1) if tc32 else (grad_output, 0)
-        max_tap = int((offsets_host[1:] - offsets_host[:-1]).max()) if k3 else 0
-        scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, max_tap, cin, cout, k3, code, _path, 1))
-        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
-        check(
-            lib.fvc_conv_wgrad_ex(
-                _ptr(x_op), x_split, _ptr(dy_op), dy_split, _ptr(topo.gather_indices), _ptr(topo.scatter_indices),
-                C.cast(offsets_host.data_ptr(), C.POINTER(C.c_int64)), topo._core.offsets_dev.data_ptr(), _ptr(out_map), int(out_map.shape[1]),
-                _ptr(topo._out_mask()), n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
+        if empty:
+            grad_weights.zero_()  # :771-777
+        elif tc_wgrad:
+            scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, 0, cin, cout, k3, code, _path, 1))
+            scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
+            check(
+                lib.fvc_conv_wgrad_ex(
+                    _ptr(x_op), x_split, _ptr(dy_op), dy_split, None, None, None, None, _ptr(out_map), int(out_map.shape[1]),
+                    _ptr(topo._out_mask()), n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
+                )
             )
-        )
+        else:
+            offsets_host = topo.offsets
+            max_tap = int((offsets_host[1:] - offsets_host[:-1]).max())
+            scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, max_tap, cin, cout, k3, code, _path, 1))
+            scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
+            check(
+                lib.fvc_conv_wgrad_ex(
+                    _ptr(x_op), x_split, _ptr(dy_op), dy_split, _ptr(topo.gather_indices), _ptr(topo.scatter_indices),
+                    C.cast(offsets_host.data_ptr(), C.POINTER(C.c_int64)), topo._core.offsets_dev.data_ptr(), _ptr(out_map), int(out_map.shape[1]),
+                    _ptr(topo._out_mask()), n_feat, n_out, cin, cout, k3, code, _path, _ptr(grad_weights), _ptr(scratch), scratch_bytes, _stream(device),
+                )
+            )
         if on_grad_weights is not None:
             on_grad_weights(grad_weights)
         # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (:803-804), output-stationary over features
         if not need_grad_features:
             grad_features = None
-        elif n_feat == 0 or n_out == 0 or topo.total_pairs == 0:
+        elif empty:
             grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
         else:
             in_map, in_mask, mirror = topo._dgrad_plan()

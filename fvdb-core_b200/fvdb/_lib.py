@@ -55,7 +55,8 @@ SIGNATURES = {
     "fvc_conv_grid_emit": (C.c_int, [_vp, _vp, _i64, _I3, _I3, _i32, _i64, _vp, _vp, _vp, _vp]),
     "fvc_grid_dilate_leaves": (C.c_int, [_GB, _vp, _i32, _I3, _I3, _vp, _vp]),
     "fvc_grid_expand_leaves": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
-    "fvc_kmap_build": (C.c_int, [_GB, _GB, _I3, _I3, _i32, _vp, _i64, _vp, _vp]),
+    "fvc_kmap_build": (C.c_int, [_GB, _GB, _I3, _I3, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "fvc_kmap_reverse_from_dense": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "fvc_kmap_csr_scratch_bytes": (_sz, [_i64, _i64]),
     "fvc_kmap_to_csr": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fvc_kmap_reverse_dense": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
     "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _i32]),
     "fvc_set_tuning": (C.c_int, [_i32, _i32]),
+    "fvc_conv_kernel_family": (_i32, [_i32, _i32, _i64, _i32, _i32, _i32]),
     "fvc_conv_weights_bytes": (_sz, [_i32, _i32, _i64, _i32, _i32]),
     "fvc_conv_prepare_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "fvc_conv_stats_blocks": (_i64, [_i64, _i32, _i32, _i64, _i32, _i32, C.POINTER(_i32)]),

@@ -215,6 +215,9 @@ def _output_zero_count(backend: _Backend) -> int | None:
     topology = _backend_topology(backend)
     if topology is None:
         return None
+    view = topology._core
+    if not topology._reversed:
+        return view.zero_degree_outputs()  # from the dense map: the CSR arrays are not materialised for a policy check
     return int((torch.bincount(topology.scatter_indices, minlength=topology.output_total_voxels) == 0).sum())
 
 
@@ -466,9 +469,9 @@ class ConvolutionPlan:
         if topology is None or isinstance(self._backend, _MatmulBackend) or not features.is_cuda or weights.ndim != 5:
             return False
         working = torch.result_type(features, weights)
-        if working not in _fvdb_cpp._DTYPE_CODE or _fvdb_cpp._path == 1:
+        if working not in _fvdb_cpp._DTYPE_CODE:
             return False
-        return int(_fvdb_cpp.lib.fvc_conv_scratch_bytes(1, 1, int(weights.shape[1]), int(weights.shape[0]), topology.kernel_volume, _fvdb_cpp._DTYPE_CODE[working])) > 0
+        return int(_fvdb_cpp.lib.fvc_conv_kernel_family(int(weights.shape[1]), int(weights.shape[0]), topology.kernel_volume, _fvdb_cpp._DTYPE_CODE[working], _fvdb_cpp._path, 0)) == 2
 
     def execute_with_stats(self, data: JaggedTensor | torch.Tensor, weights: torch.Tensor, bias: torch.Tensor | None = None):
         """``execute`` (differentiable) that also returns the per-block column sums of the output written by the kernel

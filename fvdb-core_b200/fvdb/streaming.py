@@ -66,7 +66,7 @@ class HostPipelinedConv:
             "gw_chunks": torch.empty((chunks, *weight_shape), dtype=dtype, device=dev),
             "fwd_bytes": int(lib.fvc_conv_scratch_bytes(n, rows, cin, cout, k3, code)),
             "bwd_bytes": int(lib.fvc_conv_scratch_bytes(n, rows, cout, cin, k3, code)),
-            "wg_bytes": int(lib.fvc_conv_wgrad_scratch_bytes(n, rows, topo.total_pairs, cin, cout, k3, code, 2, 1)),
+            "wg_bytes": int(lib.fvc_conv_wgrad_scratch_bytes(n, rows, 0, cin, cout, k3, code, 2, 1)),
             "x_ready": [torch.cuda.Event() for _ in range(chunks)], "dy_ready": [torch.cuda.Event() for _ in range(chunks)],
             "y_done": [torch.cuda.Event() for _ in range(chunks)], "g_done": [torch.cuda.Event() for _ in range(chunks)],
             "final": torch.cuda.Event(),
@@ -97,8 +97,7 @@ class HostPipelinedConv:
         words = (k3 + 63) // 64
         check(
             lib.fvc_conv_wgrad(
-                x.data_ptr(), dy.data_ptr() + r0 * cout * dy.element_size(), topo.gather_indices.data_ptr(), topo.scatter_indices.data_ptr(),
-                C.cast(topo.offsets.data_ptr(), C.POINTER(C.c_int64)), topo._core.offsets_dev.data_ptr(), nbr.data_ptr() + 4 * r0, pitch,
+                x.data_ptr(), dy.data_ptr() + r0 * cout * dy.element_size(), None, None, None, None, nbr.data_ptr() + 4 * r0, pitch,
                 (mask.data_ptr() + 8 * words * (r0 // 128)) if mask is not None else None, int(x.shape[0]), r1 - r0, cin, cout, k3,
                 cpp._DTYPE_CODE[x.dtype], 2, grad_w.data_ptr(), scratch.data_ptr(), scratch_bytes, stream,
             )

@@ -95,6 +95,9 @@ FVC_API int fvc_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 FVC_API int64_t fvc_launch_count(void);
 
+/* Which kernel family serves (dtype, channels, kernel volume) under `path` (0 auto / 1 CUDA-core / 2 tensor-core):
+ * returns 1 = CUDA-core kernels, 2 = tcgen05 kernels.  pass 0 = forward / dgrad, 1 = weight gradient (given a dense map). */
+FVC_API int32_t fvc_conv_kernel_family(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, int32_t pass);
 /* Experiment knob for the benchmark scripts: key 0 = pipeline-shape variant of the tensor-core forward kernel
  * (0 = the shape table's default).  Not part of the reference interface. */
 FVC_API int fvc_set_tuning(int32_t key, int32_t value);
@@ -147,9 +150,11 @@ FVC_API int fvc_conv_grid_emit(const int32_t *src_ijk, const int32_t *src_bidx, 
  * through tap k, or -1.  Forward probes fineFromCoarse on the feature grid, transposed probes
  * coarseFromFine with the divisibility test (GatherScatterDefault.cu:129-141); probes never leave the
  * output voxel's own grid (:126).  tap_counts: int64 [K^3] device, number of pairs per tap.
- * FVC_ERR_RUNTIME when either grid exceeds INT32_MAX voxels or batch sizes differ (:58-80). */
+ * FVC_ERR_RUNTIME when either grid exceeds INT32_MAX voxels or batch sizes differ (:58-80).
+ * tile_mask (may be NULL): uint64 [ceil(N_out / 128)][ceil(K^3 / 64)], the per-tile tap bitmask of fvc_kmap_tile_mask written in
+ * the same pass (zero-initialised by the call).  Asynchronous: no host synchronisation. */
 FVC_API int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_grid, const int32_t kernel_size[3],
-                   const int32_t stride[3], int32_t transposed, int32_t *nbr, int64_t pitch, int64_t *tap_counts,
+                   const int32_t stride[3], int32_t transposed, int32_t *nbr, int64_t pitch, int64_t *tap_counts, uint64_t *tile_mask,
                    fvc_stream_t stream);
 /* CSR-by-tap view of a dense map (GatherScatterDefaultTopology, GatherScatterDefault.h:59-81): per tap
  * segment, pairs ordered by output row.  offsets_dev: int64 [K^3+1] = exclusive scan of tap_counts
@@ -163,6 +168,9 @@ FVC_API int fvc_kmap_to_csr(const int32_t *nbr, int64_t pitch, int64_t n_out, in
 FVC_API int fvc_kmap_reverse_dense(const int32_t *gather, const int32_t *scatter, const int64_t *offsets_dev,
                            int64_t kernel_volume, int64_t total_pairs, int64_t n_feature, int32_t *nbr_rev,
                            int64_t pitch_rev, fvc_stream_t stream);
+/* The same reversed dense map straight from the output-stationary dense map (no CSR needed): nbr_rev[k][nbr[k][o]] = o. */
+FVC_API int fvc_kmap_reverse_from_dense(const int32_t *nbr, int64_t pitch, int64_t n_out, int64_t kernel_volume, int64_t n_feature,
+                                int32_t *nbr_rev, int64_t pitch_rev, fvc_stream_t stream);
 /* Per 128-row tile of a dense map, a bitmask over taps: bit k of mask[tile * words + (k >> 6)] (words =
  * ceil(K^3 / 64), bit index k & 63) is set iff some row of the tile has a neighbour through tap k.  The
  * tensor-core executors use it to skip whole (tile, tap) units: on planar surfaces two thirds of them are empty. */
@@ -253,7 +261,9 @@ FVC_API int fvc_split_rows(const float *x, int64_t n, int32_t channels, void *sp
  * (GatherScatterDefault.cu:806-813), written contiguous in the public layout in `dtype`;
  * fixed-order (deterministic) fp32/fp64 reduction.  offsets_host / offsets_dev: the same int64 [K^3+1]
  * CSR offsets on the host and on the device.  nbr/pitch: the output-stationary dense map of the same
- * rulebook (used by the tensor-core path; may be NULL, then the CSR path runs). */
+ * rulebook (used by the tensor-core path; may be NULL, then the CSR path runs).  When the tensor-core path runs (nbr given,
+ * dtype / channels admitted, path != 1) the CSR arguments (gather, scatter, offsets_host, offsets_dev) may all be NULL:
+ * the kernel reads the dense map only, so a plan never has to materialise the CSR view for training. */
 /* Scratch for the kernel family fvc_conv_wgrad will take: max_pairs_per_tap = the largest CSR tap segment (sizes the
  * CUDA-core partials), path as in the call, has_dense_map = whether nbr will be passed. */
 FVC_API size_t fvc_conv_wgrad_scratch_bytes(int64_t n_in, int64_t n_out, int64_t max_pairs_per_tap, int32_t cin, int32_t cout,

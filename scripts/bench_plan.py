@@ -25,10 +25,14 @@ pitch = cpp._map_pitch(n)
 nbr = torch.empty((k3, pitch), dtype=torch.int32, device=dev)
 counts = torch.empty(k3, dtype=torch.int64, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
-build = lambda: check(lib.fvc_kmap_build(grid.data.struct, grid.data.struct, i3(ks), i3(st), 0, nbr.data_ptr(), pitch, counts.data_ptr(), stream))
+fused_mask = torch.empty(((n + 127) // 128) * ((k3 + 63) // 64), dtype=torch.int64, device=dev)
+build = lambda: check(lib.fvc_kmap_build(grid.data.struct, grid.data.struct, i3(ks), i3(st), 0, nbr.data_ptr(), pitch, counts.data_ptr(), fused_mask.data_ptr(), stream))
 t = timed(build)
 wbytes = 4 * n * k3 + 128 * grid.total_leaf_nodes
-res["kmap_build_ms"] = t; res["kmap_build_GBps(write 4*N*K3 + read 128 B/leaf)"] = wbytes / t / 1e6
+res["kmap_build_ms(map + tap counts + tile mask, one kernel)"] = t; res["kmap_build_GBps(write 4*N*K3 + read 128 B/leaf)"] = wbytes / t / 1e6
+res["kmap_build_frac_of_hbm_peak"] = wbytes / t / 1e6 / bench.load_peaks()["hbm_gbs"]
+build_nomask = lambda: check(lib.fvc_kmap_build(grid.data.struct, grid.data.struct, i3(ks), i3(st), 0, nbr.data_ptr(), pitch, counts.data_ptr(), None, stream))
+res["kmap_build_ms(without the fused tile mask)"] = timed(build_nomask)
 topo = cpp.gs_build_topology(grid.data, grid.data, ks, st)
 P = topo.total_pairs
 gather = torch.empty(P, dtype=torch.int32, device=dev); scatter = torch.empty(P, dtype=torch.int32, device=dev)
@@ -41,10 +45,16 @@ t = timed(lambda: check(lib.fvc_kmap_tile_mask(nbr.data_ptr(), pitch, n, k3, mas
 res["tile_mask_ms"] = t; res["tile_mask_GBps"] = 4 * n * k3 / t / 1e6
 rev = torch.empty((k3, pitch), dtype=torch.int32, device=dev)
 t = timed(lambda: check(lib.fvc_kmap_reverse_dense(gather.data_ptr(), scatter.data_ptr(), offs.data_ptr(), k3, P, n, rev.data_ptr(), pitch, stream)))
-res["reverse_dense_ms"] = t
+res["reverse_dense_ms(from CSR)"] = t
+t = timed(lambda: check(lib.fvc_kmap_reverse_from_dense(nbr.data_ptr(), pitch, n, k3, n, rev.data_ptr(), pitch, stream)))
+res["reverse_dense_ms(from the dense map)"] = t
+assert torch.equal(mask, fused_mask), "fused tile mask differs from the stand-alone pass"
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5):
     plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid); plan._backend.topology._dgrad_plan()
-torch.cuda.synchronize(); res["plan_total_ms(python incl. syncs)"] = (time.perf_counter() - t0) / 5 * 1e3
+torch.cuda.synchronize(); res["plan_total_ms(python, no host sync inside)"] = (time.perf_counter() - t0) / 5 * 1e3
+torch.cuda.empty_cache(); torch.cuda.synchronize(); t0 = time.perf_counter()
+plan = fvdb.ConvolutionPlan.from_grid_batch(k, 1, grid, grid); plan._backend.topology._dgrad_plan()
+torch.cuda.synchronize(); res["plan_cold_ms(allocator cache emptied first)"] = (time.perf_counter() - t0) * 1e3
 res["pairs"] = P
 print(json.dumps(res))

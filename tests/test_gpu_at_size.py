@@ -136,7 +136,7 @@ def test_c2_full_size_bf16_all_of_y_grad_x_grad_w(fvdb, bench):
     x, w, _ = _inputs(grid.total_voxels, grid.total_voxels, 64, 64, (3, 3, 3), torch.bfloat16, seed=3)
     want = oracle.gs_conv(x.float(), w.float(), ref, accumulate_dtype=torch.float32)
     try:
-        for variant in (1, 2, 3, 4, 5, 6):
+        for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10):
             cpp.set_kernel_variant(variant)
             _check_half(f"y (variant {variant})", cpp.gs_conv(x.to(DEV), w.to(DEV), plan._backend.topology), want)
     finally:
