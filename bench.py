@@ -745,7 +745,7 @@ def unet_record(D: Dist, args, cfg, *, steps: int, warmup: int, graph: bool) -> 
 
     def step():
         nonlocal collectives
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=True)
         out = model(feats)
         loss = out.jdata.float().square().mean()
         loss.backward()

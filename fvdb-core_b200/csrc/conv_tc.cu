@@ -546,6 +546,13 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
             st_sum[c] = st_sq[c] = 0.f;
+        // narrow outputs keep per-thread column sums over all of the CTA's tiles and cross the warp ONCE at the end (the
+        // shuffle reduction per tile cost ~13 % of the 32-channel kernel); wide outputs reduce per tile (registers)
+        constexpr bool DEFER = COUT <= 32;
+        float df_sum[DEFER ? COUT : 1], df_sq[DEFER ? COUT : 1];
+#pragma unroll
+        for (int z = 0; z < (DEFER ? COUT : 1); ++z)
+            df_sum[z] = df_sq[z] = 0.f;
         for (int tt = 0; tt < ntiles; ++tt) {
             const int64_t row = (tile0 + tt) * TC_TILE_M + quarter * 32 + lane;
             const bool row_ok = row < n_out;
@@ -680,19 +687,40 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                         }
                     }
                     if (epi.stats) {
-                        float sq[EC];
+                        if constexpr (DEFER) {
+                            if (row_ok) {
 #pragma unroll
-                        for (int z = 0; z < EC; ++z) {
-                            v[z] = row_ok ? v[z] : 0.f;
-                            sq[z] = v[z] * v[z];
+                                for (int z = 0; z < EC; ++z) {
+                                    df_sum[c0 + z] += v[z];
+                                    df_sq[c0 + z] = fmaf(v[z], v[z], df_sq[c0 + z]);
+                                }
+                            }
+                        } else {
+                            float sq[EC];
+#pragma unroll
+                            for (int z = 0; z < EC; ++z) {
+                                v[z] = row_ok ? v[z] : 0.f;
+                                sq[z] = v[z] * v[z];
+                            }
+                            st_sum[ch] += warp_column_sum<EC>(v, lane);
+                            st_sq[ch] += warp_column_sum<EC>(sq, lane);
                         }
-                        st_sum[ch] += warp_column_sum<EC>(v, lane);
-                        st_sq[ch] += warp_column_sum<EC>(sq, lane);
                     }
                 }
             }
         }
         if (epi.stats) { // every MMA has retired (bar_accum), so the gather stages are free: [quarter][2][COUT] floats
+            if constexpr (DEFER) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    float a[EC], b[EC];
+#pragma unroll
+                    for (int z = 0; z < EC; ++z)
+                        a[z] = df_sum[ch * EC + z], b[z] = df_sq[ch * EC + z];
+                    st_sum[ch] = warp_column_sum<EC>(a, lane);
+                    st_sq[ch] = warp_column_sum<EC>(b, lane);
+                }
+            }
             float *s_stats = reinterpret_cast<float *>(smem_gen);
             if (lane < EC) {
 #pragma unroll
@@ -797,9 +825,9 @@ static inline TcShape tc_shape(int32_t cin, int32_t cout, bool split) {
     switch (cout) {
     case 16: return wide ? TcShape{8, 4, 2, 4, 1} : TcShape{8, 3, 2, 4, 0};
     case 32: return wide ? TcShape{4, 4, 2, 4, 1} : TcShape{4, 3, 2, 4, 0};
-    case 64: return wide ? TcShape{2, 3, 2, 3, 1} : TcShape{2, 3, 2, 4, 0};
+    case 64: return wide ? TcShape{2, 2, 2, 2, 1} : TcShape{2, 3, 2, 4, 0};
     case 128: return wide ? TcShape{2, 4, 2, 3, 1} : TcShape{1, 2, 2, 4, 0};
-    default: return wide ? TcShape{2, 4, 2, 4, 1} : TcShape{2, 6, 3, 4, 0};
+    default: return TcShape{2, 6, 3, 4, 0};
     }
 }
 
@@ -869,7 +897,7 @@ static int tc_forward_split(const ConvArgs &a, const void *x, const uint8_t *img
 
 static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img) {
     // experiment knob (fvc_set_tuning(0, v), scripts/bench_variants.py): alternative pipeline shapes of the two headline shapes
-    if (g_tc_variant != 0 && a.cin == a.cout && (a.cin == 64 || a.cin == 128)) {
+    if (g_tc_variant != 0 && a.cin == a.cout && (a.cin == 64 || a.cin == 128) && !a.epi.stats) { // (statistics blocks follow the default shape)
         const bool c64 = a.cin == 64;
         switch (g_tc_variant) {
         case 2: return c64 ? launch_tc_fwd<64, 64, 4, 4, 2, 4, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 4, 2, 4, false, 1>(a, x, img); // 2 CTAs / SM
@@ -877,7 +905,7 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
         case 4: return c64 ? launch_tc_fwd<64, 64, 2, 4, 2, 4, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 4, 2, 4, false, 1>(a, x, img);
         case 5: return c64 ? launch_tc_fwd<64, 64, 2, 4, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 4, 2, 2, false, 1>(a, x, img);
         case 6: return c64 ? launch_tc_fwd<64, 64, 4, 5, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 4, 2, 3, false, 1>(a, x, img);
-        case 7: return c64 ? launch_tc_fwd<64, 64, 2, 2, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 2, 1, 2, false, 1>(a, x, img); // 4 CTAs / SM
+        case 7: return c64 ? launch_tc_fwd<64, 64, 2, 3, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 2, 1, 2, false, 1>(a, x, img); // 3 CTAs / SM (64), 4 (128)
         case 8: return c64 ? launch_tc_fwd<64, 64, 1, 2, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 3, 2, 2, false, 1>(a, x, img);
         case 9: return c64 ? launch_tc_fwd<64, 64, 2, 3, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 4, 6, 2, 3, false, 1>(a, x, img);
         case 10: return c64 ? launch_tc_fwd<64, 64, 4, 3, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 3, 2, 3, false, 1>(a, x, img);
@@ -893,7 +921,7 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
     FVC_TC_LEGACY(CI, 64, 2, 3, 2)  \
     FVC_TC_LEGACY(CI, 128, 1, 2, 2) \
     FVC_TC_LEGACY(CI, 256, 2, 6, 3)
-    if (g_tc_variant == 1) { // the round-1 kernel (four producer warps share every unit, map ring) for every wide shape: A/B baseline
+    if (g_tc_variant == 1 && !a.epi.stats) { // the round-1 kernel (four producer warps share every unit, map ring) for every wide shape: A/B baseline
         FVC_TC_LEGACY_CIN(64)
         FVC_TC_LEGACY_CIN(128)
         FVC_TC_LEGACY_CIN(256)
@@ -909,9 +937,9 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
 #define FVC_TC_WIDE(CI)                        \
     FVC_TC_LAUNCH(CI, 16, 8, 4, 2, 4, false, 1) \
     FVC_TC_LAUNCH(CI, 32, 4, 4, 2, 4, false, 1) \
-    FVC_TC_LAUNCH(CI, 64, 2, 3, 2, 3, false, 1) \
+    FVC_TC_LAUNCH(CI, 64, 2, 2, 2, 2, false, 1) \
     FVC_TC_LAUNCH(CI, 128, 2, 4, 2, 3, false, 1) \
-    FVC_TC_LAUNCH(CI, 256, 2, 4, 2, 4, false, 1)
+    FVC_TC_LAUNCH(CI, 256, 2, 6, 3, 4, false, 0)
     FVC_TC_NARROW(16)
     FVC_TC_NARROW(32)
     FVC_TC_WIDE(64)

@@ -166,7 +166,7 @@ __host__ __device__ inline int64_t rows_of_block(int64_t n, int block, int grid,
 // Merge of the CTA partials (count, mean, M2) in double (Chan's formula): a CTA serves FIN_CH channels, 256 / FIN_CH threads
 // per channel walk the partials in a fixed interleaved order, then a shared-memory tree merges them; optional
 // running-stat update.
-constexpr int FIN_CH = 8, FIN_LANES = 256 / FIN_CH;
+constexpr int FIN_CH = 4, FIN_LANES = 256 / FIN_CH;
 
 __device__ __forceinline__ void chan_merge(double &cnt, double &mu, double &m2, double nb, double mb, double m2b) {
     if (nb == 0.0)
@@ -184,15 +184,28 @@ bn_stats_final_kernel(const float *__restrict__ partial, const float *__restrict
     const int tid = threadIdx.x, lane = tid / FIN_CH, ch = blockIdx.x * FIN_CH + tid % FIN_CH;
     double cnt = 0.0, mu = 0.0, m2 = 0.0;
     if (ch < c) {
-        for (int b = lane; b < grid; b += FIN_LANES) {
-            const double nb = double(rows_of_block(n, b, grid, rpb));
-            if (nb == 0.0)
-                continue;
-            const double s = partial[(int64_t(b) * 2) * c + ch], ss = partial[(int64_t(b) * 2 + 1) * c + ch];
-            const double mb = s / nb; // mean of (x - pivot) over the CTA's rows
-            double m2b = ss - s * mb;
-            m2b = m2b < 0.0 ? 0.0 : m2b;
-            chan_merge(cnt, mu, m2, nb, mb + (pivot ? double(pivot[ch]) : 0.0), m2b);
+        const double piv = pivot ? double(pivot[ch]) : 0.0;
+        // four partials per trip: the loads are independent of the (serial) merge chain, so they overlap its latency -- the
+        // convolution epilogue hands this kernel thousands of row blocks
+        for (int b0 = lane; b0 < grid; b0 += 4 * FIN_LANES) {
+            float s[4], ss[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = b0 + u * FIN_LANES;
+                s[u] = b < grid ? __ldg(partial + (int64_t(b) * 2) * c + ch) : 0.f;
+                ss[u] = b < grid ? __ldg(partial + (int64_t(b) * 2 + 1) * c + ch) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = b0 + u * FIN_LANES;
+                const double nb = b < grid ? double(rows_of_block(n, b, grid, rpb)) : 0.0;
+                if (nb == 0.0)
+                    continue;
+                const double mb = double(s[u]) / nb; // mean of (x - pivot) over the block's rows
+                double m2b = double(ss[u]) - double(s[u]) * mb;
+                m2b = m2b < 0.0 ? 0.0 : m2b;
+                chan_merge(cnt, mu, m2, nb, mb + piv, m2b);
+            }
         }
     }
     s_cnt[tid] = cnt, s_mu[tid] = mu, s_m2[tid] = m2;

@@ -100,6 +100,7 @@ class BatchNorm(nn.BatchNorm1d):
             self.num_batches_tracked.add_(1)
             if self.momentum is None:  # cumulative moving average
                 momentum = 1.0 / float(self.num_batches_tracked)
+        self._effective_momentum = momentum if (training and self.track_running_stats) else 0.0
         group = None
         if self._sync and training:
             import torch.distributed as dist
@@ -170,6 +171,19 @@ class SyncBatchNorm(BatchNorm):
         return out
 
 
+class _ZeroGradFor(torch.autograd.Function):
+    """Identity on ``rows`` that reports an exactly-zero gradient for ``param`` (a parameter whose effect cancels downstream)."""
+
+    @staticmethod
+    def forward(ctx, rows, param):  # type: ignore[override]
+        ctx.shape, ctx.dtype, ctx.device = param.shape, param.dtype, param.device
+        return rows.view_as(rows)
+
+    @staticmethod
+    def backward(ctx, grad):  # type: ignore[override]
+        return grad, torch.zeros(ctx.shape, dtype=ctx.dtype, device=ctx.device)
+
+
 def conv_bn_act(conv: _SparseConv3dBase, norm: BatchNorm, data: JaggedTensor, plan: ConvolutionPlan, residual: "JaggedTensor | None" = None,
                 final_relu: bool = False) -> JaggedTensor:
     """``norm(conv(data, plan)) + residual`` (then a ReLU if ``final_relu``: the tail of the reference's residual block,
@@ -200,8 +214,17 @@ def conv_bn_act(conv: _SparseConv3dBase, norm: BatchNorm, data: JaggedTensor, pl
                                           relu=(1 if relu else 0) | (2 if final_relu else 0))
     if fusable and training and x.shape[0] > 0:
         with record_function(f"conv_bn_act[train]({conv!r})"):
-            y, stats = plan.execute_with_stats(data, conv.weight, conv.bias)
-            out = y.jagged_like(norm._rows(y.jdata, conv_stats=stats))
+            # a bias in front of a training-mode BatchNorm cancels in the normalised output and its gradient is identically
+            # zero: the convolution runs without it (no bias add, no column-sum pass over grad_output in backward); only the
+            # running mean, which tracks mean(conv(x) + bias), has to see it
+            y, stats = plan.execute_with_stats(data, conv.weight, None)
+            rows = norm._rows(y.jdata, conv_stats=stats)
+            if conv.bias is not None:
+                if norm.track_running_stats and norm.running_mean is not None and norm._effective_momentum:
+                    with torch.no_grad():
+                        norm.running_mean.add_(conv.bias.detach().to(norm.running_mean.dtype), alpha=norm._effective_momentum)
+                rows = _ZeroGradFor.apply(rows, conv.bias)
+            out = y.jagged_like(rows)
     else:
         out = norm(conv(data, plan))
     if residual is not None:

@@ -17,6 +17,32 @@ WANT = [
 ]
 
 
+def traffic_json(rows, hdr, config: str, out_path: str):
+    """profiles/r02_ncu_traffic.json: dram read + write bytes per launch of the three hot kernels of one bench step, keyed by
+    config; bench.py reads `roofline.traffic` from it.  Capture order of a step: forward, wgrad, dgrad (wgrad runs first in
+    the backward so that its all-reduce overlaps dgrad)."""
+    import json
+    import os
+
+    name_i, rd_i, wr_i = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    units_row = rows[1]
+    fwd_like = [r for r in rows[2:] if "conv_tc_fwd" in r[name_i]]
+    wgrad = [r for r in rows[2:] if "conv_tc_wgrad" in r[name_i]]
+    val = lambda r: float(r[rd_i].replace(",", "")) * unit.get(units_row[rd_i], 1.0) + float(r[wr_i].replace(",", "")) * unit.get(units_row[wr_i], 1.0)  # noqa: E731
+    rec = {}
+    if fwd_like:
+        rec["fwd"] = val(fwd_like[0])
+    if len(fwd_like) > 1:
+        rec["dgrad"] = val(fwd_like[1])
+    if wgrad:
+        rec["wgrad"] = val(wgrad[0])
+    data = json.load(open(out_path)) if os.path.exists(out_path) else {}
+    data[config] = rec
+    data["commit"] = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump(data, open(out_path, "w"), indent=1)
+
+
 def main():
     rep = sys.argv[1]
     if len(sys.argv) > 2:
@@ -24,6 +50,8 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
+    if len(sys.argv) > 4:  # ncu_summary.py rep "header" <config> <traffic.json>
+        traffic_json(rows, hdr, sys.argv[3], sys.argv[4])
     cols = [hdr.index(w) for w in WANT if w in hdr]
     for r in rows[2:]:
         print("-----")

@@ -275,7 +275,8 @@ def test_values_and_gradients_match_oracle(fvdb, dtype, cin, cout, ks, st, tol, 
         # elementwise too, against the fp64-accumulated oracle, at the reference's own fp32 bars (forward / input gradient
         # rtol 1e-5, atol 1e-6; kernel gradient 5e-4 / 5e-4: fvdb/utils/tests/convolution_utils.py:115-136).  Those bars were
         # validated there for 1-8 feature channels and scale the gradient bars with sqrt(kernel volume / 27); rounding error grows
-        # with the square root of the number of accumulated terms, so the absolute bar scales with sqrt(terms / (8 * 27)) here
+        # with the square root of the number of accumulated terms, so the absolute bar is 2e-6 * sqrt(terms / (8 * 27)) here (the CUDA-core
+        # kernels, which serve the odd channel counts, accumulate sequentially in fp32)
         # (C1's own 32-channel 3^3 case, tests/test_gpu_at_size.py, passes the unscaled 1e-5 / 1e-6).
         topo_ref = oracle.Topology(topo.gather_indices.cpu().numpy(), topo.scatter_indices.cpu().numpy(), topo.offsets.numpy(), topo.feature_total_voxels,
                                    topo.output_total_voxels, topo.kernel_volume, topo.total_pairs, tuple(topo.kernel_size), tuple(topo.stride), topo.is_transposed)
@@ -283,8 +284,8 @@ def test_values_and_gradients_match_oracle(fvdb, dtype, cin, cout, ks, st, tol, 
         true_y = oracle.gs_conv(xd, wd, topo_ref, accumulate_dtype=torch.float64)
         true_gx, true_gw = oracle.gs_conv_backward(dyd, xd, wd, topo_ref, accumulate_dtype=torch.float64)
         k3 = k[0] * k[1] * k[2]
-        torch.testing.assert_close(y.jdata.detach().cpu().double(), true_y, rtol=1e-5, atol=1e-6 * max(1.0, (cin * k3 / 216.0) ** 0.5))
-        torch.testing.assert_close(gx.cpu().double(), true_gx, rtol=1e-5, atol=1e-6 * max(1.0, (cout * k3 / 216.0) ** 0.5))
+        torch.testing.assert_close(y.jdata.detach().cpu().double(), true_y, rtol=1e-5, atol=2e-6 * max(1.0, (cin * k3 / 216.0) ** 0.5))
+        torch.testing.assert_close(gx.cpu().double(), true_gx, rtol=1e-5, atol=2e-6 * max(1.0, (cout * k3 / 216.0) ** 0.5))
         torch.testing.assert_close(gw.cpu().double(), true_gw, rtol=5e-4 * max(1.0, (k3 / 27.0) ** 0.5), atol=5e-4 * max(1.0, (k3 / 27.0) ** 0.5))
 
 
@@ -362,8 +363,12 @@ def test_conv_bn_act_block_matches_the_separate_modules(fvdb, dtype, cin, cout, 
     assert _rel_err(out, want.float().cpu()) <= tol
     out.backward(dy), want.backward(dy)
     assert _rel_err(xa.grad, xb.grad.float().cpu()) <= tol
-    for p, q in zip(list(conv.parameters()) + list(norm.parameters()), list(conv2.parameters()) + list(norm2.parameters())):
+    for p, q in zip([conv.weight] + list(norm.parameters()), [conv2.weight] + list(norm2.parameters())):
         torch.testing.assert_close(p.grad.float(), q.grad.float(), rtol=5 * tol, atol=5 * tol * float(q.grad.float().abs().max()))
+    # a bias in front of a training-mode BatchNorm cancels: the fused block reports its gradient as exactly zero, the separate
+    # modules compute rounding noise around zero
+    assert int(torch.count_nonzero(conv.bias.grad)) == 0
+    assert float(conv2.bias.grad.float().abs().max()) <= 2e-2 * float(dy.float().abs().sum(0).max())
     torch.testing.assert_close(norm.running_mean.float(), norm2.running_mean.float(), rtol=1e-2, atol=1e-3)
     torch.testing.assert_close(norm.running_var.float(), norm2.running_var.float(), rtol=1e-2, atol=1e-3)
     conv.eval(), norm.eval(), conv2.eval(), norm2.eval()
