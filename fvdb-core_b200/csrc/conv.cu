@@ -51,8 +51,8 @@ int32_t fvc_conv_kernel_family(int32_t cin, int32_t cout, int64_t kernel_volume,
 }
 
 int fvc_set_tuning(int32_t key, int32_t value) {
-    FVC_REQUIRE(key == 0, FVC_ERR_VALUE, "unknown tuning key %d", key);
-    g_tc_variant = value;
+    FVC_REQUIRE(key == 0 || key == 1, FVC_ERR_VALUE, "unknown tuning key %d", key);
+    (key == 0 ? g_tc_variant : g_wgrad_variant) = value;
     return FVC_OK;
 }
 

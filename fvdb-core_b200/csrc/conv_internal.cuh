@@ -75,6 +75,7 @@ int64_t tc_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int32_t dtype,
 int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t stream);
 // experiment knob (fvc_set_tuning): pipeline shape variant of the forward kernel, 0 = default
 extern int g_tc_variant;
+extern int g_wgrad_variant; // same for the weight-gradient kernel (key 1)
 // opt in to > 48 KB of dynamic shared memory once per (kernel instantiation, device)
 template <typename K> inline int ensure_dynamic_smem(K kernel, size_t bytes, std::atomic<unsigned long long> &done_mask) {
     int dev = 0;

@@ -25,6 +25,8 @@ namespace fvc {
 
 using namespace tc;
 
+int g_wgrad_variant = 0;
+
 constexpr int WG_PW = 4;                  // gather-producer warps (also the epilogue warps)
 constexpr int WG_WARP_MMA = WG_PW;        // warp WG_PW + 1 streams the kernel map
 constexpr int WG_THREADS = (WG_PW + 2) * 32;
@@ -35,7 +37,7 @@ constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 reduction-side el
 // a dY row narrower than 64 channels is zero-padded to one 128-byte row (N = 64 for the MMA, extra columns unused).
 // CTAS: co-resident CTAs per SM (TMEM columns are split between them).  Two half-size CTAs hide each other's per-unit
 // hand-off latency on the narrow-output shapes, where a dY tile is cheap to load twice.
-template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1> struct TcWgradCfg {
+template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1, int BSTG = 0> struct TcWgradCfg {
     static constexpr int G = CIN >= 64 ? 1 : 64 / CIN;      // taps per A block
     static constexpr int CB = CIN >= 64 ? CIN / 64 : 1;     // A channel blocks per tap (group)
     static constexpr int CPT = CIN >= 64 ? 8 : CIN / 8;     // 16-byte chunks one tap contributes to a row
@@ -47,7 +49,7 @@ template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1> struc
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * NPAD; // TMEM columns per unit (SPLIT: main | small-term accumulator)
     static constexpr int TMEM_COLS = 512 / CTAS;            // this CTA's share of the SM's tensor memory
     static constexpr int MAX_UNITS = TMEM_COLS / ACC_COLS;  // accumulators that fit
-    static constexpr int BSTAGES = ((SPLIT && COUT >= 128) || CTAS > 1) ? 1 : 2;
+    static constexpr int BSTAGES = BSTG ? BSTG : (((SPLIT && COUT >= 128) || CTAS > 1) ? 1 : 2); // dY tile buffers
     static constexpr int RING = G == 4 ? 4 : 8;             // kernel-map ring depth
     static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;    // 128 int32 per tap (+ a 16-byte pad so packed taps sit on different banks)
     static constexpr int RING_BYTES = 2 * G * SUB_STRIDE;   // two blocks x G taps
@@ -78,12 +80,12 @@ __device__ __forceinline__ void lds_v4x2(uint32_t addr, int (&v)[8]) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr + 16) : "memory");
 }
 
-template <int CIN, int COUT, int STAGES, bool SPLIT, int CTAS>
+template <int CIN, int COUT, int STAGES, bool SPLIT, int CTAS, int BSTG>
 __global__ void __launch_bounds__(WG_THREADS, CTAS)
 conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
                      int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
                      int tiles_per_chunk, int seg_tiles, uint32_t idesc, float *__restrict__ partial) {
-    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS>;
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS, BSTG>;
     constexpr int G = Cfg::G, CB = Cfg::CB, CPT = Cfg::CPT, NB = Cfg::NB, NPAD = Cfg::NPAD, RING = Cfg::RING;
     constexpr int NS = Cfg::NS, XS = Cfg::XS, YS = Cfg::YS, ACC = Cfg::ACC_COLS, BSTAGES = Cfg::BSTAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -393,11 +395,15 @@ struct WgradPlan {
 constexpr int WG_SPLIT_SEG_TILES = 32; // fp32: drain the accumulators every 32 row tiles (<= 256 full-magnitude MMA steps)
 
 // outputs up to 64 channels (bf16 / f16; 64 TMEM columns per accumulator) run two half-TMEM CTAs per SM
-static inline int wgrad_ctas(int cout, bool split) { return (!split && cout <= 64) ? 2 : 1; }
+static inline int wgrad_ctas(int cin, int cout, bool split) {
+    if (g_wgrad_variant == 2 && cin == 64 && cout == 64 && !split)
+        return 1; // experiment: one full-TMEM CTA per SM
+    return (!split && cout <= 64) ? 2 : 1;
+}
 
 static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split) {
     WgradPlan p;
-    const int ctas = wgrad_ctas(cout, split);
+    const int ctas = wgrad_ctas(cin, cout, split);
     const int total_blocks = cin >= 64 ? k3 * (cin / 64) : int(ceil_div(k3, 64 / cin));
     const int total_units = (total_blocks + 1) / 2;
     const int max_units = (512 / ctas) / ((split ? 2 : 1) * (cout >= 64 ? cout : 64));
@@ -417,11 +423,12 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split
 
 // tc_split_rows (conv_tc.cu) writes the bf16 split rows of an fp32 operand
 
-template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1>
+template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1, int BSTG = 0>
 static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, float *partial) {
-    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS>;
-    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT, CTAS>;
-    FVC_REQUIRE(CTAS == wgrad_ctas(COUT, SPLIT), FVC_ERR_RUNTIME, "weight-gradient plan / kernel shape mismatch");
+    using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS, BSTG>;
+    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT, CTAS, BSTG>;
+    const int ctas_planned = wgrad_ctas(CIN, COUT, SPLIT);
+    FVC_REQUIRE(CTAS == ctas_planned, FVC_ERR_RUNTIME, "weight-gradient plan / kernel shape mismatch");
     static std::atomic<unsigned long long> configured{0}; // per instantiation, one bit per device
     const int rc_attr = ensure_dynamic_smem(kernel, Cfg::SMEM, configured);
     if (rc_attr)
@@ -505,6 +512,11 @@ int tc_wgrad(const WgradArgs &a) {
 #undef FVC_WGS_CASE
         return set_error(FVC_ERR_UNSUPPORTED, "no fp32 tensor-core wgrad kernel for channels %d -> %d", a.cin, a.cout);
     }
+    // experiment knob (fvc_set_tuning(1, v)): the 64 -> 64 shape with two dY tile buffers per CTA (v = 1) / three gather stages (v = 2)
+    if (g_wgrad_variant == 1 && a.cin == 64 && a.cout == 64)
+        return launch_tc_wgrad<64, 64, 2, false, 2, 2>(a, a.x, a.dy, partial);
+    if (g_wgrad_variant == 2 && a.cin == 64 && a.cout == 64)
+        return launch_tc_wgrad<64, 64, 4, false, 1, 2>(a, a.x, a.dy, partial);
 #define FVC_WG_CASE(CI, CO, S)       \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S>(a, a.x, a.dy, partial);

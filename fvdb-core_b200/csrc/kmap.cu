@@ -202,6 +202,135 @@ kmap_build_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transpose
     }
 }
 
+// Fast path of the same build: every forward map (any stride) and the unit-stride transposed maps whose probe box fits the
+// cache.  ncu on the general kernel showed it issue-bound (~130 warp instructions per (32 voxels, tap): 64-bit mask
+// arithmetic, per-probe leaf-index and address arithmetic, one shared-memory atomic per tap).  Here
+//   * a cached source leaf is re-encoded once per output leaf as [x word][32-bit half] entries {mask half, row of the half's
+//     first voxel} -- one 8-byte shared load answers a probe with 32-bit arithmetic, a missing leaf is an all-zero mask;
+//   * taps run as nested (t0, t1, t2) loops, so the x / y parts of the probe, of the leaf index and of the bit position are
+//     hoisted, and the store pointer advances by the pitch;
+//   * kernels of <= 32 taps keep the per-tap pair counts in registers (lane k owns tap k) instead of shared-memory atomics.
+template <bool SMALL32>
+__global__ void __launch_bounds__(KM_THREADS)
+kmap_build_fast_kernel(FvcGridBatch feat, FvcGridBatch out, Geometry g, int transposed, int32_t *__restrict__ nbr,
+                       int64_t pitch, unsigned long long *__restrict__ tap_counts, unsigned long long *__restrict__ tile_mask, int mask_words) {
+    __shared__ __align__(16) uint2 s_entry[KM_WARPS][KM_MAX_NB][8][2]; // {mask half, batch-cumulative row before the half}
+    __shared__ int s_leaf[KM_WARPS][KM_MAX_NB];
+    __shared__ uint16_t s_vox[KM_WARPS][512];
+    __shared__ uint32_t s_cnt[SMALL32 ? 1 : KM_MAX_TAPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k3 = int(g.volume);
+    if (!SMALL32) {
+        for (int k = tid; k < k3; k += KM_THREADS)
+            s_cnt[k] = 0;
+        __syncthreads();
+    }
+    uint32_t my_count = 0; // SMALL32: pairs of tap `lane` seen by this warp
+    const int leaf_id = blockIdx.x * KM_WARPS + warp;
+    if (leaf_id < out.num_leaves) {
+        const FvcLeaf *L = out.leaves + leaf_id;
+        const int b = __ldg(&L->batch);
+        const int origin[3] = {__ldg(&L->origin[0]), __ldg(&L->origin[1]), __ldg(&L->origin[2])};
+        const int base = __ldg(&L->base);
+        const int cnt = __ldg(&L->count);
+        const LeafBox box = probe_box(g, origin, transposed);
+        // (1) lanes walk the tree in parallel, one source leaf each
+        for (int t = lane; t < box.total; t += 32) {
+            const int c = t % box.n[2], bb = (t / box.n[2]) % box.n[1], a = t / (box.n[2] * box.n[1]);
+            s_leaf[warp][t] = find_leaf(feat, b, (box.lmin[0] + a) << 3, (box.lmin[1] + bb) << 3, (box.lmin[2] + c) << 3);
+        }
+        // (2) compact the output leaf's active voxels: rank inside the leaf == row - base.  Lane l scans 16 bits.
+        {
+            const int w = lane >> 2, shift = (lane & 3) * 16;
+            const uint64_t m = __ldg(L->mask + w);
+            const int before = int(__ldg(L->prefix + w)) + __popcll(m & ((1ull << shift) - 1ull));
+            uint32_t bits = uint32_t(m >> shift) & 0xFFFFu;
+            for (int r = before; bits; bits &= bits - 1u, ++r)
+                s_vox[warp][r] = uint16_t((w << 6) + shift + __ffs(bits) - 1);
+        }
+        __syncwarp();
+        // (3) re-encode every source leaf: entry (leaf, x word w, half h) <- one 8-byte mask word + its prefix count
+        for (int e = lane; e < box.total * 8; e += 32) {
+            const int li = e >> 3, w = e & 7, leaf = s_leaf[warp][li];
+            uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+            if (leaf >= 0) {
+                const FvcLeaf *S = feat.leaves + leaf;
+                const uint64_t m = __ldg(S->mask + w);
+                const uint32_t first = uint32_t(__ldg(&S->base)) + uint32_t(__ldg(S->prefix + w));
+                lo = make_uint2(uint32_t(m), first);
+                hi = make_uint2(uint32_t(m >> 32), first + uint32_t(__popc(uint32_t(m))));
+            }
+            s_entry[warp][li][w][0] = lo;
+            s_entry[warp][li][w][1] = hi;
+        }
+        __syncwarp();
+        // (4) probes
+        const uint2 *entries = &s_entry[warp][0][0][0];
+        const int dir = transposed ? -1 : 1; // forward: S * c - pad + t;  unit-stride transposed: c + pad - t
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int j = j0 + lane;
+            const bool has = j < cnt;
+            const int n = has ? s_vox[warp][j] : 0;
+            int c0[3] = {origin[0] + (n >> 6), origin[1] + ((n >> 3) & 7), origin[2] + (n & 7)};
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                c0[d] = transposed ? c0[d] + g.pad[d] : g.s[d] * c0[d] - g.pad[d];
+            const int64_t tile_lo = (int64_t(base) + j0) >> 7;
+            const unsigned in_lo = __ballot_sync(0xffffffffu, ((int64_t(base) + j) >> 7) == tile_lo);
+            unsigned long long taps_lo = 0ull, taps_hi = 0ull;
+            int32_t *dst = nbr + base + j; // + k * pitch
+            int k = 0;
+            for (int t0 = 0; t0 < g.k[0]; ++t0) {
+                const int px = c0[0] + dir * t0;
+                const int ex = (((px >> 3) - box.lmin[0]) * box.n[1]) , wx = px & 7;
+                for (int t1 = 0; t1 < g.k[1]; ++t1) {
+                    const int py = c0[1] + dir * t1;
+                    const int exy = (ex + ((py >> 3) - box.lmin[1])) * box.n[2] - box.lmin[2];
+                    const int half = (py >> 2) & 1, ybit = (py & 3) << 3;
+                    for (int t2 = 0; t2 < g.k[2]; ++t2, ++k, dst += pitch) {
+                        const int pz = c0[2] + dir * t2;
+                        const int li = exy + (pz >> 3);
+                        const uint2 en = entries[((li << 3) + wx) * 2 + half];
+                        const int bit = ybit | (pz & 7);
+                        const bool hit = has && ((en.x >> bit) & 1u);
+                        const int val = hit ? int(en.y + uint32_t(__popc(en.x & ((1u << bit) - 1u)))) : -1;
+                        if (has)
+                            *dst = val;
+                        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                        if (SMALL32) {
+                            if (lane == k)
+                                my_count += uint32_t(__popc(hits));
+                        } else if (lane == 0 && hits) {
+                            atomicAdd(&s_cnt[k], uint32_t(__popc(hits)));
+                        }
+                        if (tile_mask) {
+                            taps_lo |= (unsigned long long)((hits & in_lo) != 0u) << (k & 63);
+                            taps_hi |= (unsigned long long)((hits & ~in_lo) != 0u) << (k & 63);
+                            if ((k & 63) == 63 || k == k3 - 1) {
+                                if (lane == 0 && taps_lo)
+                                    atomicOr(tile_mask + tile_lo * mask_words + (k >> 6), taps_lo);
+                                if (lane == 0 && taps_hi)
+                                    atomicOr(tile_mask + (tile_lo + 1) * mask_words + (k >> 6), taps_hi);
+                                taps_lo = taps_hi = 0ull;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (SMALL32) {
+        if (lane < k3 && my_count)
+            atomicAdd(tap_counts + lane, (unsigned long long)my_count);
+    } else {
+        __syncthreads();
+        for (int k = tid; k < k3; k += KM_THREADS)
+            if (s_cnt[k])
+                atomicAdd(tap_counts + k, (unsigned long long)s_cnt[k]);
+    }
+}
+
 // ---- CSR-by-tap view ------------------------------------------------------------------------------
 constexpr int CSR_THREADS = 256;
 constexpr int CSR_ROWS_PER_THREAD = 8;
@@ -480,9 +609,26 @@ int fvc_kmap_build(const FvcGridBatch *feature_grid, const FvcGridBatch *output_
     }
     if (output_grid->num_leaves == 0)
         return FVC_OK;
-    kmap_build_kernel<<<unsigned(ceil_div(output_grid->num_leaves, KM_WARPS)), KM_THREADS, 0, stream>>>(
-        *feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, reinterpret_cast<unsigned long long *>(tap_counts),
-        reinterpret_cast<unsigned long long *>(tile_mask), mask_words);
+    // fast path: forward maps of any stride and unit-stride transposed maps whose probe box (the same for every leaf: origins
+    // are multiples of 8) fits the per-warp leaf cache, with at most KM_MAX_TAPS taps
+    bool fast = g.volume <= KM_MAX_TAPS && (!transposed || (g.s[0] == 1 && g.s[1] == 1 && g.s[2] == 1));
+    if (fast) {
+        int total = 1;
+        for (int d = 0; d < 3; ++d) {
+            // widest case over the origin's residue: span of probes of one leaf, in leaves (+1 for an unaligned start)
+            const int span = transposed ? (7 + g.k[d] - 1) : (g.s[d] * 7 + g.k[d] - 1);
+            total *= span / 8 + 2;
+        }
+        fast = total <= KM_MAX_NB;
+    }
+    const unsigned grid = unsigned(ceil_div(output_grid->num_leaves, KM_WARPS));
+    unsigned long long *counts = reinterpret_cast<unsigned long long *>(tap_counts), *tmask = reinterpret_cast<unsigned long long *>(tile_mask);
+    if (fast && g.volume <= 32)
+        kmap_build_fast_kernel<true><<<grid, KM_THREADS, 0, stream>>>(*feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, counts, tmask, mask_words);
+    else if (fast)
+        kmap_build_fast_kernel<false><<<grid, KM_THREADS, 0, stream>>>(*feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, counts, tmask, mask_words);
+    else
+        kmap_build_kernel<<<grid, KM_THREADS, 0, stream>>>(*feature_grid, *output_grid, g, transposed ? 1 : 0, nbr, pitch, counts, tmask, mask_words);
     FVC_LAUNCH_CHECK();
     return FVC_OK;
 }

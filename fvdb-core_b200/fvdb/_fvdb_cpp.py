@@ -30,9 +30,10 @@ def set_conv_path(name: str) -> None:
     _path = _FORCED_PATH[name]
 
 
-def set_kernel_variant(variant: int) -> None:
-    """Benchmark knob (fvc_set_tuning key 0): pipeline-shape variant of the tensor-core forward kernel; 0 = default."""
-    check(lib.fvc_set_tuning(0, int(variant)))
+def set_kernel_variant(variant: int, wgrad: bool = False) -> None:
+    """Benchmark knob (fvc_set_tuning): pipeline-shape variant of the tensor-core forward (key 0) / weight-gradient (key 1)
+    kernel; 0 = default."""
+    check(lib.fvc_set_tuning(1 if wgrad else 0, int(variant)))
 
 
 def _stream(device: torch.device) -> int:

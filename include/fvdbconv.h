@@ -98,8 +98,8 @@ FVC_API int64_t fvc_launch_count(void);
 /* Which kernel family serves (dtype, channels, kernel volume) under `path` (0 auto / 1 CUDA-core / 2 tensor-core):
  * returns 1 = CUDA-core kernels, 2 = tcgen05 kernels.  pass 0 = forward / dgrad, 1 = weight gradient (given a dense map). */
 FVC_API int32_t fvc_conv_kernel_family(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, int32_t pass);
-/* Experiment knob for the benchmark scripts: key 0 = pipeline-shape variant of the tensor-core forward kernel
- * (0 = the shape table's default).  Not part of the reference interface. */
+/* Experiment knob for the benchmark scripts: key 0 = pipeline-shape variant of the tensor-core forward kernel, key 1 = of the
+ * weight-gradient kernel (0 = the shape table's default).  Not part of the reference interface. */
 FVC_API int fvc_set_tuning(int32_t key, int32_t value);
 
 /* -------- geometry (host-only; replaces ConvolutionGeometry.h:30-207) ----------------------------- */

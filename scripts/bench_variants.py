@@ -57,3 +57,28 @@ cpp.set_kernel_variant(0)
 if len(sys.argv) > 3:
     with open(sys.argv[3], "w") as fh:
         json.dump(rows, fh, indent=1)
+# weight-gradient shapes (key 1) on the same batch
+if cin == cout == 64:
+    dy = torch.randn((n, cout), device=dev).to(dtype)
+    wrows, wref = [], None
+    for variant in (0, 1, 2):
+        cpp.set_kernel_variant(variant, wgrad=True)
+        f = lambda: cpp.gs_conv_backward(dy, x, w, topo, need_grad_features=False)[1]  # noqa: E731
+        gw = f()
+        torch.cuda.synchronize()
+        wref = gw if wref is None else wref
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            f()
+        b.record()
+        torch.cuda.synchronize()
+        wrows.append({"wgrad_variant": variant, "wgrad_ms": a.elapsed_time(b) / 10, "max_abs_diff_vs_first": float((gw.float() - wref.float()).abs().max())})
+        print(json.dumps(wrows[-1]), flush=True)
+    cpp.set_kernel_variant(0, wgrad=True)
+    if len(sys.argv) > 3:
+        with open(sys.argv[3].replace(".json", "_wgrad.json"), "w") as fh:
+            json.dump(wrows, fh, indent=1)
