@@ -49,8 +49,10 @@ template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1, int B
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * NPAD; // TMEM columns per unit (SPLIT: main | small-term accumulator)
     static constexpr int TMEM_COLS = 512 / CTAS;            // this CTA's share of the SM's tensor memory
     static constexpr int MAX_UNITS = TMEM_COLS / ACC_COLS;  // accumulators that fit
-    static constexpr int BSTAGES = BSTG ? BSTG : (((SPLIT && COUT >= 128) || CTAS > 1) ? 1 : 2); // dY tile buffers
-    static constexpr int RING = G == 4 ? 4 : 8;             // kernel-map ring depth
+    // dY tile buffers.  Two let the next tile's dY load overlap this tile's MMAs (one buffer stalls every tile on the load:
+    // 64 -> 64 on C2 0.615 -> 0.549 ms, profiles/r02_variants_c2_wgrad.json); the packed 16-channel shape has no room for it
+    static constexpr int BSTAGES = BSTG ? BSTG : (((SPLIT && COUT >= 128) || (CTAS > 1 && CIN < 32)) ? 1 : 2);
+    static constexpr int RING = G >= 2 ? 4 : 8;             // kernel-map ring depth
     static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;    // 128 int32 per tap (+ a 16-byte pad so packed taps sit on different banks)
     static constexpr int RING_BYTES = 2 * G * SUB_STRIDE;   // two blocks x G taps
     static constexpr int A_STAGE = 2 * WG_BLOCK_BYTES;
@@ -514,7 +516,7 @@ int tc_wgrad(const WgradArgs &a) {
     }
     // experiment knob (fvc_set_tuning(1, v)): the 64 -> 64 shape with two dY tile buffers per CTA (v = 1) / three gather stages (v = 2)
     if (g_wgrad_variant == 1 && a.cin == 64 && a.cout == 64)
-        return launch_tc_wgrad<64, 64, 2, false, 2, 2>(a, a.x, a.dy, partial);
+        return launch_tc_wgrad<64, 64, 2, false, 2, 1>(a, a.x, a.dy, partial); // round-1 shape: one dY buffer
     if (g_wgrad_variant == 2 && a.cin == 64 && a.cout == 64)
         return launch_tc_wgrad<64, 64, 4, false, 1, 2>(a, a.x, a.dy, partial);
 #define FVC_WG_CASE(CI, CO, S)       \
