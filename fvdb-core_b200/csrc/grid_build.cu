@@ -16,10 +16,15 @@ struct Add4 {
     }
 };
 
+struct TileRange { // smallest / largest root-tile coordinate of the batch per axis (see "single-pass key" below)
+    int lo[3], hi[3];
+};
+
 struct BuildScratch {
     uint64_t *key_a, *key_b;
     uint32_t *idx_a, *idx_b;
     int4 *scan;
+    TileRange *range;
     void *cub_temp;
     size_t cub_bytes;
     size_t total;
@@ -49,6 +54,7 @@ static BuildScratch carve(void *scratch, int64_t n) {
     s.idx_a = reinterpret_cast<uint32_t *>(take(m * 4));
     s.idx_b = reinterpret_cast<uint32_t *>(take(m * 4));
     s.scan = reinterpret_cast<int4 *>(take(m * 16 + 16));
+    s.range = reinterpret_cast<TileRange *>(take(sizeof(TileRange)));
     s.cub_bytes = cub_temp_bytes(n > 0 ? n : 1);
     s.cub_temp = take(s.cub_bytes);
     s.total = off;
@@ -67,6 +73,57 @@ __device__ __forceinline__ uint64_t key_lo(int x, int y, int z) {
 __device__ __forceinline__ uint64_t key_hi(int b, int x, int y) {
     const uint64_t tx = uint64_t((x >> 12) + (1 << 19)), ty = uint64_t((y >> 12) + (1 << 19));
     return (uint64_t(b) << 32) | (tx << 12) | (ty >> 8);
+}
+
+// ---- single-pass key: when every grid of the batch spans at most 64 root tiles per axis (262 144 voxels) the whole order
+// fits ONE 64-bit key  [grid : 10][tx - tx_min : 6][ty - ty_min : 6][tz - tz_min : 6][upper : 15][lower : 12][leaf : 9]
+// (subtracting the batch-wide minimum tile keeps the lexicographic order), i.e. one 8-digit radix sort instead of 8 + 6 digits
+// and one encode pass instead of two.  The tile range is found on the device; whether it fits is read back with the counts
+// the build synchronises on anyway, and the rare wide batch re-runs the two-pass path.
+__global__ void tile_range_init_kernel(TileRange *r) {
+    if (threadIdx.x < 3) {
+        r->lo[threadIdx.x] = INT32_MAX;
+        r->hi[threadIdx.x] = INT32_MIN;
+    }
+}
+
+__global__ void tile_range_kernel(const int32_t *__restrict__ ijk, int64_t n, TileRange *__restrict__ range) {
+    int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int t = ijk[3 * i + d] >> 12;
+            lo[d] = t < lo[d] ? t : lo[d];
+            hi[d] = t > hi[d] ? t : hi[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int a = __shfl_xor_sync(0xffffffffu, lo[d], o), b = __shfl_xor_sync(0xffffffffu, hi[d], o);
+            lo[d] = a < lo[d] ? a : lo[d];
+            hi[d] = b > hi[d] ? b : hi[d];
+        }
+        if ((threadIdx.x & 31) == 0 && lo[d] <= hi[d]) {
+            atomicMin(&range->lo[d], lo[d]);
+            atomicMax(&range->hi[d], hi[d]);
+        }
+    }
+}
+
+__global__ void encode64_kernel(const int32_t *__restrict__ ijk, const int32_t *__restrict__ bidx, int64_t n, const TileRange *__restrict__ range,
+                                uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    const int t0 = range->lo[0], t1 = range->lo[1], t2 = range->lo[2];
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const int x = ijk[3 * i], y = ijk[3 * i + 1], z = ijk[3 * i + 2];
+        const uint64_t tx = uint64_t((x >> 12) - t0) & 63ull, ty = uint64_t((y >> 12) - t1) & 63ull, tz = uint64_t((z >> 12) - t2) & 63ull;
+        const uint64_t up = uint64_t(((((x >> 7) & 31) << 5) | ((y >> 7) & 31)) << 5 | ((z >> 7) & 31));
+        const uint64_t lo = uint64_t(((((x >> 3) & 15) << 4) | ((y >> 3) & 15)) << 4 | ((z >> 3) & 15));
+        const uint64_t vx = uint64_t(((x & 7) << 6) | ((y & 7) << 3) | (z & 7));
+        keys[i] = (uint64_t(bidx ? bidx[i] : 0) << 54) | (tx << 48) | (ty << 42) | (tz << 36) | (up << 21) | (lo << 9) | vx;
+        idx[i] = uint32_t(i);
+    }
 }
 
 __global__ void encode_lo_kernel(const int32_t *__restrict__ ijk, int64_t n, uint64_t *__restrict__ keys,
@@ -213,35 +270,76 @@ int fvc_grid_build_count(const int32_t *ijk, const int32_t *bidx, int64_t n, int
     FVC_REQUIRE(scratch && scratch_bytes >= s.total, FVC_ERR_RUNTIME, "grid build scratch too small: %zu < %zu",
                 scratch_bytes, s.total);
     const int block = 256, grid = grid_for(n, block);
-    encode_lo_kernel<<<grid, block, 0, stream>>>(ijk, n, s.key_a, s.idx_a);
+    tile_range_init_kernel<<<1, 32, 0, stream>>>(s.range);
     FVC_LAUNCH_CHECK();
-    cub::DoubleBuffer<uint64_t> keys(s.key_a, s.key_b);
-    cub::DoubleBuffer<uint32_t> vals(s.idx_a, s.idx_b);
-    size_t temp = s.cub_bytes;
-    FVC_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, keys, vals, n, 0, 64, stream));
-    g_launch_count.fetch_add(1);
-    uint32_t *idx_sorted = vals.Current();
-    uint32_t *idx_other = vals.Alternate();
-    // second (most significant) pass; keys are regenerated from the permuted inputs
-    encode_hi_kernel<<<grid, block, 0, stream>>>(ijk, bidx, n, idx_sorted, s.key_a);
+    tile_range_kernel<<<grid, block, 0, stream>>>(ijk, n, s.range);
     FVC_LAUNCH_CHECK();
-    cub::DoubleBuffer<uint64_t> keys2(s.key_a, s.key_b);
-    cub::DoubleBuffer<uint32_t> vals2(idx_sorted, idx_other);
-    temp = s.cub_bytes;
-    FVC_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, keys2, vals2, n, 0, 42, stream));
-    g_launch_count.fetch_add(1);
-    // keep the final permutation in idx_a so that stage 2 finds it
-    if (vals2.Current() != s.idx_a)
-        FVC_CUDA(cudaMemcpyAsync(s.idx_a, vals2.Current(), size_t(n) * 4, cudaMemcpyDeviceToDevice, stream));
-    // head flags reuse key_b as storage? no: flags are int4, written straight into s.scan then scanned in place
-    head_flags_kernel<<<grid, block, 0, stream>>>(ijk, bidx, n, s.idx_a, s.scan);
-    FVC_LAUNCH_CHECK();
-    temp = s.cub_bytes;
-    FVC_CUDA(cub::DeviceScan::InclusiveScan(s.cub_temp, temp, s.scan, s.scan, Add4(), n, stream));
-    g_launch_count.fetch_add(1);
+    auto two_pass = [&]() -> int {
+        encode_lo_kernel<<<grid, block, 0, stream>>>(ijk, n, s.key_a, s.idx_a);
+        FVC_LAUNCH_CHECK();
+        cub::DoubleBuffer<uint64_t> keys(s.key_a, s.key_b);
+        cub::DoubleBuffer<uint32_t> vals(s.idx_a, s.idx_b);
+        size_t temp = s.cub_bytes;
+        FVC_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, keys, vals, n, 0, 64, stream));
+        g_launch_count.fetch_add(1);
+        uint32_t *idx_sorted = vals.Current();
+        uint32_t *idx_other = vals.Alternate();
+        // second (most significant) pass; keys are regenerated from the permuted inputs
+        encode_hi_kernel<<<grid, block, 0, stream>>>(ijk, bidx, n, idx_sorted, s.key_a);
+        FVC_LAUNCH_CHECK();
+        cub::DoubleBuffer<uint64_t> keys2(s.key_a, s.key_b);
+        cub::DoubleBuffer<uint32_t> vals2(idx_sorted, idx_other);
+        temp = s.cub_bytes;
+        FVC_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, keys2, vals2, n, 0, 42, stream));
+        g_launch_count.fetch_add(1);
+        // keep the final permutation in idx_a so that stage 2 finds it
+        if (vals2.Current() != s.idx_a)
+            FVC_CUDA(cudaMemcpyAsync(s.idx_a, vals2.Current(), size_t(n) * 4, cudaMemcpyDeviceToDevice, stream));
+        return FVC_OK;
+    };
+    auto one_pass = [&]() -> int {
+        encode64_kernel<<<grid, block, 0, stream>>>(ijk, bidx, n, s.range, s.key_a, s.idx_a);
+        FVC_LAUNCH_CHECK();
+        cub::DoubleBuffer<uint64_t> keys(s.key_a, s.key_b);
+        cub::DoubleBuffer<uint32_t> vals(s.idx_a, s.idx_b);
+        size_t temp = s.cub_bytes;
+        FVC_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, keys, vals, n, 0, 64, stream));
+        g_launch_count.fetch_add(1);
+        if (vals.Current() != s.idx_a)
+            FVC_CUDA(cudaMemcpyAsync(s.idx_a, vals.Current(), size_t(n) * 4, cudaMemcpyDeviceToDevice, stream));
+        return FVC_OK;
+    };
+    auto flags_and_counts = [&](int4 *totals, TileRange *range_host) -> int {
+        head_flags_kernel<<<grid, block, 0, stream>>>(ijk, bidx, n, s.idx_a, s.scan);
+        FVC_LAUNCH_CHECK();
+        size_t temp = s.cub_bytes;
+        FVC_CUDA(cub::DeviceScan::InclusiveScan(s.cub_temp, temp, s.scan, s.scan, Add4(), n, stream));
+        g_launch_count.fetch_add(1);
+        FVC_CUDA(cudaMemcpyAsync(totals, s.scan + (n - 1), sizeof(int4), cudaMemcpyDeviceToHost, stream));
+        if (range_host)
+            FVC_CUDA(cudaMemcpyAsync(range_host, s.range, sizeof(TileRange), cudaMemcpyDeviceToHost, stream));
+        FVC_CUDA(cudaStreamSynchronize(stream));
+        return FVC_OK;
+    };
     int4 totals;
-    FVC_CUDA(cudaMemcpyAsync(&totals, s.scan + (n - 1), sizeof(int4), cudaMemcpyDeviceToHost, stream));
-    FVC_CUDA(cudaStreamSynchronize(stream));
+    TileRange range_host;
+    int rc = one_pass();
+    if (rc)
+        return rc;
+    rc = flags_and_counts(&totals, &range_host);
+    if (rc)
+        return rc;
+    bool narrow = true;
+    for (int d = 0; d < 3; ++d)
+        narrow = narrow && (int64_t(range_host.hi[d]) - range_host.lo[d] < 64);
+    if (!narrow) { // a batch wider than 64 root tiles on some axis: the 64-bit key wrapped -- redo with the 106-bit key
+        rc = two_pass();
+        if (rc)
+            return rc;
+        rc = flags_and_counts(&totals, nullptr);
+        if (rc)
+            return rc;
+    }
     counts_host[0] = totals.x;
     counts_host[1] = totals.y;
     counts_host[2] = totals.z;
