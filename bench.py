@@ -172,6 +172,9 @@ def algorithmic_bytes(P, n_in, n_out, cin, cout, k3, s):
         "fwd": P * cin * s + n_out * cout * s + 4 * P + k3 * cin * cout * s,
         "dgrad": P * cout * s + n_in * cin * s + 4 * P + k3 * cin * cout * s,
         "wgrad": P * (cin + cout) * s + 8 * P + 4 * k3 * cin * cout,
+        # narrow layers: dgrad AND wgrad off ONE gather of grad_output (csrc/conv_tc_bwd.cu) -- the gathered rows and the map are
+        # charged once, the feature rows are read once as contiguous tiles, grad_features written once
+        "bwd_fused": P * cout * s + 2 * n_in * cin * s + 4 * P + k3 * cin * cout * s + 4 * k3 * cin * cout,
     }
 
 
@@ -181,6 +184,7 @@ def compulsory_bytes(P, n_in, n_out, cin, cout, k3, s):
         "fwd": n_in * cin * s + n_out * cout * s + 4 * P + k3 * cin * cout * s,
         "dgrad": n_out * cout * s + n_in * cin * s + 4 * P + k3 * cin * cout * s,
         "wgrad": n_in * cin * s + n_out * cout * s + 4 * P + 4 * k3 * cin * cout,
+        "bwd_fused": n_out * cout * s + 2 * n_in * cin * s + 4 * P + k3 * cin * cout * s + 4 * k3 * cin * cout,
     }
 
 
@@ -190,6 +194,7 @@ def kernel_rooflines(kern_ms, P, n_in, n_out, cin, cout, k3, s, peaks):
     out = {}
     for name, ms in kern_ms.items():
         t = ms * 1e-3
+        flops = (2.0 if name != "bwd_fused" else 4.0) * P * cin * cout
         hbm_t, tensor_t = abytes[name] / (peaks["hbm_gbs"] * 1e9), flops / (peaks["tflops"] * 1e12)
         bound = "hbm" if hbm_t >= tensor_t else "tensor"
         achieved = abytes[name] / t / 1e9 if bound == "hbm" else flops / t / 1e12
@@ -199,8 +204,10 @@ def kernel_rooflines(kern_ms, P, n_in, n_out, cin, cout, k3, s, peaks):
                      "algorithmic_bytes": abytes[name], "flops": flops,
                      "compulsory": {"bytes": cbytes[name], "floor_ms": comp_t * 1e3, "frac": comp_t / t,
                                     "note": "every row once + map + weights at the HBM peak (or the FLOPs at the tensor peak, whichever is slower)"}}
-    roof_ms = sum(max(abytes[nm] / (peaks["hbm_gbs"] * 1e9), flops / (peaks["tflops"] * 1e12)) for nm in kern_ms) * 1e3
-    comp_ms = sum(out[nm]["compulsory"]["floor_ms"] for nm in kern_ms)
+    # the kernels one step launches: forward + the fused backward where it serves the layer, else forward + dgrad + wgrad
+    in_step = ("fwd", "bwd_fused") if "bwd_fused" in kern_ms else ("fwd", "dgrad", "wgrad")
+    roof_ms = sum(max(abytes[nm] / (peaks["hbm_gbs"] * 1e9), out[nm]["flops"] / (peaks["tflops"] * 1e12)) for nm in in_step) * 1e3
+    comp_ms = sum(out[nm]["compulsory"]["floor_ms"] for nm in in_step)
     return out, roof_ms, comp_ms
 
 
@@ -475,6 +482,8 @@ def conv_workload(D: Dist, cfg: dict, args, *, want_e2e: bool, want_gpu_baseline
         "dgrad": timed(lambda: cpp._run_conv(dy, w_bwd, in_map, n, n, cout, cin, k3, None, in_mask), reps),
         "wgrad": timed(lambda: cpp.gs_conv_backward(dy, x, w, topo, need_grad_features=False), reps),
     }
+    if cpp._fused_backward and dtype in (torch.float16, torch.bfloat16) and int(cpp.lib.fvc_conv_kernel_family(cin, cout, k3, cpp._DTYPE_CODE[dtype], 0, 2)) == 2:
+        kern_ms["bwd_fused"] = timed(lambda: cpp.gs_conv_backward(dy, x, w, topo), reps)  # (its weight image and partial reduction included)
     peaks = load_peaks()
     s = x.element_size()
     per_kernel, roof_ms, comp_ms = kernel_rooflines(kern_ms, P, n, n, cin, cout, k3, s, peaks)
@@ -591,7 +600,8 @@ def conv_record(D: Dist, cfg: dict, res: dict, *, steps: int, warmup: int, stron
     ms, e2e_ms = mx[0], mx[1]
     total_n, total_p = sm[0], sm[1]
     per_kernel = res["per_kernel"]
-    dominant = max(per_kernel, key=lambda nm: per_kernel[nm]["ms"])
+    in_step = ("fwd", "bwd_fused") if "bwd_fused" in per_kernel else ("fwd", "dgrad", "wgrad")  # the kernels a step launches
+    dominant = max(in_step, key=lambda nm: per_kernel[nm]["ms"])
     roof = dict(per_kernel[dominant])
     traffic = ncu_traffic(config_name) if D.world == 1 else None
     roof.update({"kernel": dominant, "traffic": (traffic["bytes"].get(dominant) if traffic else None), "traffic_source": traffic["source"] if traffic else None,

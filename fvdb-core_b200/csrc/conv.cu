@@ -46,8 +46,28 @@ extern "C" {
 int32_t fvc_conv_kernel_family(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, int32_t pass) {
     if (path == 1)
         return 1;
+    if (pass == 2) // fused backward (cin / cout are the PUBLIC weight dimensions)
+        return tc_bwd_fused_supported(cin, cout, kernel_volume, dtype) && tc_forward_supported(cout, cin, kernel_volume, dtype) ? 2 : 1;
     const bool tc = pass == 0 ? tc_forward_supported(cin, cout, kernel_volume, dtype) : tc_wgrad_supported(cin, cout, kernel_volume, dtype);
     return tc ? 2 : 1;
+}
+
+size_t fvc_conv_backward_fused_scratch_bytes(int64_t n_in, int32_t cin, int32_t cout, int64_t kernel_volume) {
+    return tc_bwd_fused_scratch_bytes(n_in, cin, cout, kernel_volume);
+}
+
+int fvc_conv_backward_fused(const void *grad_output, const void *features, const void *w_prepared_transposed, const int32_t *in_map, int64_t pitch,
+                            const uint64_t *in_tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume,
+                            int32_t dtype, int32_t flip_taps, void *grad_features, void *grad_w, void *scratch, size_t scratch_bytes,
+                            fvc_stream_t stream) {
+    int rc = check_common(features, w_prepared_transposed, n_in, n_out, cin, cout, kernel_volume, dtype, "fvc_conv_backward_fused");
+    if (rc)
+        return rc;
+    FVC_REQUIRE(n_in > 0 && n_out > 0 && kernel_volume > 0, FVC_ERR_RUNTIME, "fvc_conv_backward_fused: empty problem (the caller zero-fills, GatherScatterDefault.cu:771-777)");
+    FVC_REQUIRE(grad_output && in_map && grad_features && grad_w, FVC_ERR_RUNTIME, "fvc_conv_backward_fused: null pointer");
+    BwdFusedArgs a{grad_output, features, w_prepared_transposed, in_map, pitch, in_tile_mask, n_in, n_out, cin, cout, int32_t(kernel_volume), dtype,
+                   flip_taps ? 1 : 0, grad_features, grad_w, scratch, scratch_bytes, reinterpret_cast<cudaStream_t>(stream)};
+    return tc_bwd_fused(a);
 }
 
 int fvc_set_tuning(int32_t key, int32_t value) {

@@ -54,6 +54,27 @@ struct WgradArgs {
     bool x_split = false, dy_split = false; // fp32 only: operands already are bf16 split rows (fvc_split_rows)
 };
 
+// Fused backward (conv_tc_bwd.cu): dgrad and wgrad from one gather of grad_output, narrow channels only
+struct BwdFusedArgs {
+    const void *dy;     // grad_output rows [n_out][cout]
+    const void *x;      // feature rows [n_in][cin]
+    const void *w_img;  // fvc_conv_prepare_weights(transpose = 1, flip_taps) image for the tensor-core path
+    const int32_t *map; // input-stationary dense map [K^3][pitch]: for input row i and tap k the output row, or -1
+    int64_t pitch;
+    const uint64_t *tile_mask; // its per-tile tap bitmask (may be null)
+    int64_t n_in, n_out;
+    int32_t cin, cout, k3, dtype;
+    int32_t flip_taps; // the map is the forward map of a symmetric plan walked with mirrored taps: dW taps are stored mirrored
+    void *dx;          // [n_in][cin]
+    void *grad_w;      // [Cout][Cin][K^3] public layout
+    void *scratch;
+    size_t scratch_bytes;
+    cudaStream_t stream;
+};
+bool tc_bwd_fused_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
+size_t tc_bwd_fused_scratch_bytes(int64_t n_in, int32_t cin, int32_t cout, int64_t k3);
+int tc_bwd_fused(const BwdFusedArgs &a);
+
 // CUDA-core path: every dtype, every channel count
 int simt_forward(const ConvArgs &a);
 size_t simt_wgrad_scratch_bytes(int64_t total_pairs_max_tap, int32_t cin, int32_t cout, int64_t k3, int32_t dtype);

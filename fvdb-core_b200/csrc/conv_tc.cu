@@ -89,6 +89,9 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static_assert(TILES * ACC_COLS <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
     static_assert(MODE == 0 ? PW == 4 : (PW >= 2 && PW <= 4 && G == 1), "producer warps / mode");
     static_assert(WARPS >= 4, "the epilogue needs one warp per TMEM lane quarter");
+    // warp-per-unit producers hold PW units in flight: with fewer stages a warp could meet a stage barrier two phases behind,
+    // which a parity wait cannot tell from a ready one
+    static_assert(MODE == 0 || STAGES >= PW, "warp-per-unit producers need at least PW stages");
 };
 
 __device__ __forceinline__ float load_any_f(const void *p, int64_t i, int dtype) {

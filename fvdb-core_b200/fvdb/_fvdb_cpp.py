@@ -9,6 +9,7 @@ reached through ``ctypes``.  There is no CPU path: CPU tensors are rejected.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Sequence
 
 import torch
@@ -28,6 +29,18 @@ def set_conv_path(name: str) -> None:
     """Force the CUDA-core ("simt") or tcgen05 ("tc") kernel family, or "auto" (default)."""
     global _path
     _path = _FORCED_PATH[name]
+
+
+# measured (profiles/r02_time_fused.jsonl): the fused kernel ties or loses against the two separate kernels on 4 of 5 narrow shapes (its
+# single persistent CTA per SM is bound by shared-memory bandwidth: one write + two MMA reads of every gathered block), so it is opt-in
+_fused_backward = os.environ.get("FVC_FUSED_BACKWARD", "0") == "1"
+
+
+def set_fused_backward(enabled: bool) -> None:
+    """Experiment switch: serve narrow half-precision layers' backward with ONE kernel (fvc_conv_backward_fused) or with the
+    separate weight-gradient and dgrad kernels."""
+    global _fused_backward
+    _fused_backward = bool(enabled)
 
 
 def set_kernel_variant(variant: int, wgrad: bool = False) -> None:
@@ -758,8 +771,24 @@ def _backward(grad_output, features, weights, topo, name, want_transposed, on_gr
         tc32 = working == torch.float32 and not empty and tc_wgrad and _tensor_core_fp32(cin, cout, k3) and _tensor_core_fp32(cout, cin, k3)
         x_op, x_split = (features_split, 1) if (tc32 and features_split is not None) else (features, 0)
         dy_op, dy_split = (split_rows(grad_output), 1) if tc32 else (grad_output, 0)
+        # narrow half-precision layers: grad_features AND grad_weights from one gather of grad_output (conv_tc_bwd.cu)
+        fused = (_fused_backward and need_grad_features and not empty and working in (torch.float16, torch.bfloat16)
+                 and int(lib.fvc_conv_kernel_family(cin, cout, k3, code, _path, 2)) == 2)
+        grad_features = None
         if empty:
             grad_weights.zero_()  # :771-777
+        elif fused:
+            in_map, in_mask, mirror = topo._dgrad_plan()
+            wt = _prepare_weights(weights, working, transpose=True, flip_taps=mirror)
+            grad_features = torch.empty((n_feat, cin), dtype=working, device=device)
+            scratch_bytes = int(lib.fvc_conv_backward_fused_scratch_bytes(n_feat, cin, cout, k3))
+            scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device)
+            check(
+                lib.fvc_conv_backward_fused(
+                    _ptr(grad_output), _ptr(features), wt.data_ptr(), _ptr(in_map), int(in_map.shape[1]), _ptr(in_mask), n_feat, n_out, cin, cout, k3, code,
+                    int(mirror), grad_features.data_ptr(), grad_weights.data_ptr(), scratch.data_ptr(), scratch_bytes, _stream(device),
+                )
+            )
         elif tc_wgrad:
             scratch_bytes = int(lib.fvc_conv_wgrad_scratch_bytes(n_feat, n_out, 0, cin, cout, k3, code, _path, 1))
             scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=device) if scratch_bytes else None
@@ -784,8 +813,8 @@ def _backward(grad_output, features, weights, topo, name, want_transposed, on_gr
         if on_grad_weights is not None:
             on_grad_weights(grad_weights)
         # dgrad: dX[i] = sum_k dY[in_map[k][i]] . W[k]^T  (:803-804), output-stationary over features
-        if not need_grad_features:
-            grad_features = None
+        if not need_grad_features or fused:
+            pass
         elif empty:
             grad_features = torch.zeros((n_feat, cin), dtype=working, device=device)  # :771-777
         else:

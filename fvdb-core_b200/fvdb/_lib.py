@@ -69,6 +69,8 @@ SIGNATURES = {
     "fvc_conv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _sz, _vp]),
     "fvc_conv_wgrad_scratch_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _i32]),
     "fvc_set_tuning": (C.c_int, [_i32, _i32]),
+    "fvc_conv_backward_fused_scratch_bytes": (_sz, [_i64, _i32, _i32, _i64]),
+    "fvc_conv_backward_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "fvc_conv_kernel_family": (_i32, [_i32, _i32, _i64, _i32, _i32, _i32]),
     "fvc_conv_weights_bytes": (_sz, [_i32, _i32, _i64, _i32, _i32]),
     "fvc_conv_prepare_weights": (C.c_int, [_vp, C.POINTER(_i64 * 5), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),

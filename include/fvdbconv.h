@@ -96,7 +96,8 @@ FVC_API int fvc_device_info(int *sm_count, int *cc_major, int *cc_minor);
 FVC_API int64_t fvc_launch_count(void);
 
 /* Which kernel family serves (dtype, channels, kernel volume) under `path` (0 auto / 1 CUDA-core / 2 tensor-core):
- * returns 1 = CUDA-core kernels, 2 = tcgen05 kernels.  pass 0 = forward / dgrad, 1 = weight gradient (given a dense map). */
+ * returns 1 = CUDA-core kernels, 2 = tcgen05 kernels.  pass 0 = forward / dgrad, 1 = weight gradient (given a dense map),
+ * 2 = the fused backward (fvc_conv_backward_fused; cin / cout = the public weight dimensions). */
 FVC_API int32_t fvc_conv_kernel_family(int32_t cin, int32_t cout, int64_t kernel_volume, int32_t dtype, int32_t path, int32_t pass);
 /* Experiment knob for the benchmark scripts: key 0 = pipeline-shape variant of the tensor-core forward kernel, key 1 = of the
  * weight-gradient kernel (0 = the shape table's default).  Not part of the reference interface. */
@@ -278,6 +279,17 @@ FVC_API int fvc_conv_wgrad_ex(const void *x, int32_t x_is_split, const void *dy,
                       const int32_t *scatter, const int64_t *offsets_host, const int64_t *offsets_dev, const int32_t *nbr, int64_t pitch,
                       const uint64_t *tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout, int64_t kernel_volume,
                       int32_t dtype, int32_t path, void *grad_w, void *scratch, size_t scratch_bytes, fvc_stream_t stream);
+
+/* Fused backward for narrow layers (cin, cout in {16, 32}, f16 / bf16, K^3 <= 128; fvc_conv_kernel_family(..., pass = 2) == 2):
+ * grad_features AND grad_w from ONE gather of grad_output (both sums of GatherScatterDefault.cu:803-807 consume the same
+ * gathered rows).  in_map / in_tile_mask: the INPUT-stationary dense map (fvc_kmap_reverse_from_dense, or the forward map of a
+ * same-grid stride-1 odd-kernel plan with flip_taps = 1) and its tile mask; w_prepared_transposed: fvc_conv_prepare_weights
+ * (transpose = 1, the same flip_taps).  cin / cout are the public weight dimensions.  Deterministic (no atomics). */
+FVC_API size_t fvc_conv_backward_fused_scratch_bytes(int64_t n_in, int32_t cin, int32_t cout, int64_t kernel_volume);
+FVC_API int fvc_conv_backward_fused(const void *grad_output, const void *features, const void *w_prepared_transposed, const int32_t *in_map,
+                            int64_t pitch, const uint64_t *in_tile_mask, int64_t n_in, int64_t n_out, int32_t cin, int32_t cout,
+                            int64_t kernel_volume, int32_t dtype, int32_t flip_taps, void *grad_features, void *grad_w, void *scratch,
+                            size_t scratch_bytes, fvc_stream_t stream);
 
 /* -------- stride-1 generated topologies by leaf-mask morphology (fast path of conv_grid / conv_transpose_grid;
  *          replaces the NanoVDB DilateGrid route of ops/BuildGridForConv.cu:392-463) --------------------------------

@@ -13,6 +13,8 @@ WANT = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__m_xbar2l1tex_read_bytes.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_ldgsts.sum", "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
 ]
 
@@ -47,8 +49,11 @@ def main():
     rep = sys.argv[1]
     if len(sys.argv) > 2:
         print(sys.argv[2])
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    if rep.endswith(".csv"):  # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = [r for r in csv.reader(out.splitlines()) if len(r) > 8]
     hdr, units = rows[0], rows[1]
     if len(sys.argv) > 4:  # ncu_summary.py rep "header" <config> <traffic.json>
         traffic_json(rows, hdr, sys.argv[3], sys.argv[4])

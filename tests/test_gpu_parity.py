@@ -289,6 +289,53 @@ def test_values_and_gradients_match_oracle(fvdb, dtype, cin, cout, ks, st, tol, 
         torch.testing.assert_close(gw.cpu().double(), true_gw, rtol=5e-4 * max(1.0, (k3 / 27.0) ** 0.5), atol=5e-4 * max(1.0, (k3 / 27.0) ** 0.5))
 
 
+@pytest.mark.parametrize("dtype,cin,cout,ks,st", [(torch.bfloat16, 16, 16, 5, 1), (torch.bfloat16, 32, 32, 3, 1), (torch.float16, 16, 32, 3, 1),
+                                                   (torch.bfloat16, 32, 16, 3, 1), (torch.bfloat16, 32, 32, 2, 2), (torch.bfloat16, 16, 16, (3, 5, 1), (1, 2, 1)),
+                                                   (torch.float16, 16, 16, 3, 2)])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_fused_backward_matches_separate_kernels_and_oracle(fvdb, dtype, cin, cout, ks, st, transposed):
+    """fvc_conv_backward_fused (narrow layers: dgrad and wgrad off one gather of grad_output) against the two separate
+    kernels on the same inputs, and both against the oracle; large enough that every persistent CTA walks several tiles, with a
+    far-away second grid so some tiles reach only a few taps."""
+    from fvdb import _fvdb_cpp
+    from fvdb.utils.synthetic import sphere_shell
+
+    _FUSED_DEFAULT = _fvdb_cpp._fused_backward
+    shell = sphere_shell(target=60000, domain=160, seed=11, device="cpu").numpy()
+    source = _grid(fvdb, [shell, _random_batch(7, n=4000, extent=12, batches=1)[0] + 500])
+    factory = fvdb.ConvolutionPlan.from_grid_batch_transposed if transposed else fvdb.ConvolutionPlan.from_grid_batch
+    same_topology = (not transposed) and oracle.normalize_3d(st) == (1, 1, 1)
+    plan = factory(kernel_size=ks, stride=st, source_grid=source, target_grid=source if same_topology else None, acknowledge_incomplete_coverage=True)
+    topo = plan._backend.topology
+    k = oracle.normalize_3d(ks)
+    k3 = k[0] * k[1] * k[2]
+    assert int(_fvdb_cpp.lib.fvc_conv_kernel_family(cin, cout, k3, _fvdb_cpp._DTYPE_CODE[dtype], 0, 2)) == 2
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn((source.total_voxels, cin), generator=gen).to(dtype).to(DEV)
+    w = ((torch.rand((cout, cin, *k), generator=gen) * 2 - 1) / (cin * k3) ** 0.5).to(dtype).to(DEV)
+    dy = torch.randn((plan.target_grid_batch.total_voxels, cout), generator=gen).to(dtype).to(DEV)
+    backward = _fvdb_cpp.gs_conv_transpose_backward if transposed else _fvdb_cpp.gs_conv_backward
+    _fvdb_cpp.set_fused_backward(True)
+    gx_f, gw_f = backward(dy, x, w, topo)  # (the first call also builds the lazily derived input-stationary map)
+    before = int(_fvdb_cpp.lib.fvc_launch_count())
+    gx_f2, gw_f2 = backward(dy, x, w, topo)
+    fused_launches = int(_fvdb_cpp.lib.fvc_launch_count()) - before
+    assert torch.equal(gx_f, gx_f2) and torch.equal(gw_f, gw_f2)  # no atomics: run-to-run deterministic
+    _fvdb_cpp.set_fused_backward(False)
+    try:
+        before = int(_fvdb_cpp.lib.fvc_launch_count())
+        gx_s, gw_s = backward(dy, x, w, topo)
+        separate_launches = int(_fvdb_cpp.lib.fvc_launch_count()) - before
+    finally:
+        _fvdb_cpp.set_fused_backward(_FUSED_DEFAULT)
+    assert fused_launches < separate_launches  # the fused kernel really served the first call
+    # same products, fp32 accumulation in a different order, one rounding to the half type at the end
+    assert _rel_err(gx_f, gx_s.float().cpu()) <= 4e-3 and _rel_err(gw_f, gw_s.float().cpu()) <= 4e-3
+    _, want_gx, want_gw = _oracle_run(topo, x, w, dy)
+    assert _rel_err(gx_f, want_gx) <= 2e-2 and _rel_err(gw_f, want_gw) <= 2e-2
+    torch.testing.assert_close(gx_f.float().cpu(), want_gx, rtol=2e-2, atol=2e-2 * float(want_gx.abs().max()))
+
+
 @pytest.mark.parametrize("dtype,cin,cout,tol", [(torch.bfloat16, 64, 64, 2e-2), (torch.bfloat16, 128, 32, 2e-2), (torch.float16, 64, 128, 2e-2),
                                                  (torch.bfloat16, 32, 64, 2e-2), (torch.bfloat16, 16, 16, 2e-2), (torch.float32, 64, 64, 2e-5),
                                                  (torch.float32, 32, 128, 2e-5), (torch.bfloat16, 256, 256, 2e-2)])
