@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "fvdb" / "libfvdbconv.so"
 OBJ = HERE / "build"
-SOURCES = ["abi.cu", "grid_build.cu", "kmap.cu", "weights.cu", "conv.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc_bwd.cu", "norm.cu", "pool.cu", "grid_morph.cu"]
+SOURCES = ["abi.cu", "grid_build.cu", "kmap.cu", "weights.cu", "conv.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc_bwd.cu", "conv_tc_ts.cu", "norm.cu", "pool.cu", "grid_morph.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

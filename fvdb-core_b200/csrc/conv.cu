@@ -121,7 +121,7 @@ int64_t fvc_conv_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int64_t 
             *rows_per_block = 0;
         return 0; // the fused statistics exist on the tensor-core path only
     }
-    return tc_stats_blocks(n_out, cin, cout, dtype, rows_per_block);
+    return tc_stats_blocks(n_out, cin, cout, kernel_volume, dtype, rows_per_block);
 }
 
 int fvc_conv_forward_ex(const void *x, int32_t x_is_split, const void *w_prepared, const FvcConvEpilogue *epilogue, void *y, const int32_t *nbr,

@@ -92,7 +92,11 @@ size_t tc_weight_image_bytes(int32_t cin, int32_t cout, int64_t k3, int32_t dtyp
 int tc_prepare_weights(const void *weights, const int64_t strides[5], int32_t dtype_in, int32_t cout, int32_t cin, int32_t k0, int32_t k1,
                        int32_t k2, int32_t transpose, int32_t flip_taps, int32_t dtype, void *image, cudaStream_t stream);
 // rows of the per-CTA statistics partials the forward kernel writes for n_out output rows (Epilogue::stats), and rows per block
-int64_t tc_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int32_t dtype, int32_t *rows_per_block);
+int64_t tc_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype, int32_t *rows_per_block);
+// narrow half-precision layers: gathered operand through tensor memory (conv_tc_ts.cu); same weight image as conv_tc.cu
+bool tc_ts_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype);
+int64_t tc_ts_stats_blocks(int64_t n_out, int32_t *rows_per_block);
+int tc_ts_forward(const ConvArgs &a, const void *x, const uint8_t *img);
 int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t stream);
 // experiment knob (fvc_set_tuning): pipeline shape variant of the forward kernel, 0 = default
 extern int g_tc_variant;

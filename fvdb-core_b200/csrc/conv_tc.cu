@@ -35,6 +35,7 @@
 // scripts/exp_accum_precision.py), so the full-magnitude chain must stay as short as the bf16 one.
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
+#include "tc_math.cuh"
 
 #include <cstring>
 
@@ -191,43 +192,6 @@ __global__ void tc_split_rows_kernel(const float *__restrict__ x, int64_t n, int
         for (int i = 0; i < 3; ++i)
             *reinterpret_cast<uint4 *>(xs + (row * 3 + i) * c + ch) = make_uint4(packed[i][0], packed[i][1], packed[i][2], packed[i][3]);
     }
-}
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b, bool bf16) {
-    if (bf16) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        return *reinterpret_cast<uint32_t *>(&h);
-    }
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-__device__ __forceinline__ float half_to_float(uint16_t v, bool bf16) {
-    return bf16 ? __bfloat162float(*reinterpret_cast<__nv_bfloat16 *>(&v)) : __half2float(*reinterpret_cast<__half *>(&v));
-}
-__device__ __forceinline__ void unpack_half2(uint32_t p, bool bf16, float &a, float &b) {
-    if (bf16) {
-        a = __uint_as_float(p << 16), b = __uint_as_float(p & 0xFFFF0000u);
-    } else {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&p));
-        a = f.x, b = f.y;
-    }
-}
-
-// Column sums across the 32 lanes of a warp by recursive halving: on return lane l holds the sum over all lanes of
-// column (l & (N - 1)) in v[0]  (N - 1 (+1) shuffles instead of 5 N).
-template <int N> __device__ __forceinline__ float warp_column_sum(float (&v)[N], int lane) {
-#pragma unroll
-    for (int h = N / 2; h >= 1; h >>= 1) {
-        const bool upper = (lane & h) != 0;
-#pragma unroll
-        for (int i = 0; i < h; ++i) {
-            const float send = upper ? v[i] : v[i + h], keep = upper ? v[i + h] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-        }
-    }
-    if (N < 32)
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
-    return v[0];
 }
 
 // x: feature rows (SPLIT: the bf16 split rows [N][3][CIN]); bias / residual / y: in the output dtype (SPLIT: fp32)
@@ -845,7 +809,15 @@ bool tc_forward_supported(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) 
     return k3 >= 1 && k3 <= 64 * TC_MASK_WORDS && units <= (split ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS);
 }
 
-int64_t tc_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int32_t dtype, int32_t *rows_per_block) {
+// Variant 12 (fvc_set_tuning(0, 12)) serves narrow half-precision layers with the tensor-memory executor (conv_tc_ts.cu).  Measured
+// (profiles/r02_ts_executor.md): it cuts the L2 -> SM traffic to the compulsory bytes but, at ~230 dependent instructions per
+// (warp, unit) with 16 gather warps per SM, only ties the shared-memory kernels (faster on 16 -> 32, slower on 32 -> 32 and on
+// BASELINE.json configs[4]), so those stay the default.
+static inline bool takes_ts(int32_t cin, int32_t cout, int64_t k3, int32_t dtype) { return g_tc_variant == 12 && tc_ts_supported(cin, cout, k3, dtype); }
+
+int64_t tc_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype, int32_t *rows_per_block) {
+    if (takes_ts(cin, cout, k3, dtype))
+        return tc_ts_stats_blocks(n_out, rows_per_block);
     const int tiles = tc_shape(cin, cout, dtype == FVC_F32).tiles;
     if (rows_per_block)
         *rows_per_block = tiles * TC_TILE_M;
@@ -899,6 +871,8 @@ static int tc_forward_split(const ConvArgs &a, const void *x, const uint8_t *img
 }
 
 static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img) {
+    if (takes_ts(a.cin, a.cout, a.k3, a.dtype))
+        return tc_ts_forward(a, x, img);
     // experiment knob (fvc_set_tuning(0, v), scripts/bench_variants.py): alternative pipeline shapes of the two headline shapes
     if (g_tc_variant != 0 && a.cin == a.cout && (a.cin == 64 || a.cin == 128) && !a.epi.stats) { // (statistics blocks follow the default shape)
         const bool c64 = a.cin == 64;

@@ -37,6 +37,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             __trap();
     }
 }
+// Same wait for roles that idle for long stretches (an epilogue waiting for a whole tile, an MMA issuer waiting for its gather
+// group): sleep between polls so that the spin does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
+    uint32_t done = 0;
+    long long start = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done)
+            break;
+        __nanosleep(sleep_ns);
+        const long long now = clock64();
+        if (start == 0)
+            start = now;
+        else if (now - start > 4000000000ll)
+            __trap();
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -61,6 +86,14 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, int 
 // 16-byte LDGSTS; src_bytes = 0 zero-fills (a missing neighbour row)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// 16-byte LDGSTS through L1 (rows gathered again by a neighbouring tap / tile of the same CTA can hit)
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 // the calling thread's arrival on `bar` fires when all of its prior cp.async have landed (no pending-count
 // increment: the arrival is one of the barrier's expected arrivals); the thread itself never blocks
@@ -97,6 +130,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 lanes = rows, one 32-bit column per two 16-bit reduction elements) was
+// written by tcgen05.st; no shared-memory read for A
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -124,6 +169,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+// registers -> TMEM: thread i of the warp writes 32 consecutive 32-bit columns of lane (base_lane + i)
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------------

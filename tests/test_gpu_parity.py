@@ -456,6 +456,52 @@ def test_forward_pipeline_variants_agree_with_oracle(fvdb, variant, channels):
     assert torch.equal(y, default)  # same per-row MMA order in every shape
 
 
+@pytest.mark.parametrize("dtype,cin,cout,ks,st", [(torch.bfloat16, 16, 16, 5, 1), (torch.bfloat16, 32, 32, 3, 1), (torch.float16, 16, 32, 3, 1),
+                                                   (torch.bfloat16, 32, 16, 2, 2), (torch.bfloat16, 16, 16, (3, 5, 1), (1, 2, 1))])
+def test_tensor_memory_executor_matches_shared_memory_kernels(fvdb, dtype, cin, cout, ks, st):
+    """Variant 12: narrow layers with the gathered operand written to tensor memory by tcgen05.st (conv_tc_ts.cu) -- forward, dgrad,
+    the fused block epilogue and its statistics -- against the default kernels and the oracle."""
+    from fvdb.utils.synthetic import sphere_shell
+
+    cpp = fvdb._fvdb_cpp
+    source = _grid(fvdb, [sphere_shell(target=60_000, domain=160, seed=11, device="cpu").numpy(), _random_batch(7, n=4000, extent=12, batches=1)[0] + 500])
+    same = oracle.normalize_3d(st) == (1, 1, 1)
+    plan = fvdb.ConvolutionPlan.from_grid_batch(ks, st, source, source if same else None, acknowledge_incomplete_coverage=True)
+    topo = plan._backend.topology
+    k = oracle.normalize_3d(ks)
+    gen = torch.Generator().manual_seed(23)
+    n_out = plan.target_grid_batch.total_voxels
+    x = torch.randn((source.total_voxels, cin), generator=gen).to(dtype).to(DEV)
+    w = ((torch.rand((cout, cin, *k), generator=gen) * 2 - 1) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(dtype).to(DEV)
+    dy = torch.randn((n_out, cout), generator=gen).to(dtype).to(DEV)
+    bias = torch.randn(cout, generator=gen).to(dtype).to(DEV)
+    scale, shift = torch.rand(cout, generator=gen).to(DEV) + 0.5, torch.randn(cout, generator=gen).to(DEV)
+    res = torch.randn((n_out, cout), generator=gen).to(dtype).to(DEV)
+
+    def run():
+        y = cpp.gs_conv(x, w, topo, bias)
+        gx, _ = cpp.gs_conv_backward(dy, x, w, topo)
+        z, stats = cpp.gs_conv(x, w, topo, bias, scale=scale, shift=shift, residual=res, relu=3, want_stats=True)
+        sums = stats.partial.double().sum(0)  # [2, cout]: column sums / sums of squares of the stored values
+        return y, gx, z, sums
+
+    want = run()
+    try:
+        cpp.set_kernel_variant(12)
+        got = run()
+        again = run()
+    finally:
+        cpp.set_kernel_variant(0)
+    want_y, want_gx, _ = _oracle_run(topo, x, w, dy)
+    assert _rel_err(got[0].float() - bias.float(), want_y) <= 2e-2 and _rel_err(got[1], want_gx) <= 2e-2
+    for a, b, c in zip(got[:3], want[:3], again[:3]):
+        assert _rel_err(a, b.float().cpu()) <= 4e-3  # same products, fp32 sums in another order, one rounding at the end
+        assert torch.equal(a, c)  # deterministic
+    torch.testing.assert_close(got[3], want[3], rtol=2e-3, atol=2e-3 * float(want[3].abs().max()))
+    z = got[2].double()
+    torch.testing.assert_close(got[3], torch.stack([z.sum(0), (z * z).sum(0)]), rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("transposed", [False, True])
 @pytest.mark.parametrize("stride", [1, (2, 2, 2)])
 def test_gradcheck_fp64(fvdb, transposed, stride):
