@@ -67,10 +67,17 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static constexpr int ACC_COLS = (SPLIT ? 2 : 1) * COUT;  // TMEM columns per tile (SPLIT: main | small-term accumulator)
     static constexpr int TMEM_COLS = tmem_cols_for(TILES * ACC_COLS);
     static constexpr bool RING = MODE == 0;                  // kernel-map ring + streamer warp
+    // MODE 3: NP pipelines per CTA -- each = two producer warps, its own MMA-issuing warp, its own gather stages and its own
+    // TILES / NP tiles -- sharing ONE stream of weight chunks: a fat CTA loads every live chunk once for all of its tiles
+    // (the L2 -> SM traffic of a wide layer is mostly re-streamed weights) without falling back on one
+    // issuing thread for the whole SM (~850 dependent cycles per unit, profiles/r02_ts_executor.md)
+    static constexpr int NP = MODE == 3 ? PW / 2 : 1;
+    static constexpr int SP = STAGES / NP;                   // gather stages per pipeline
+    static constexpr int TP = TILES / NP;                    // tiles per pipeline
     // unit-list capacity: packed taps (Cin < 64) never exceed 128 groups x 8 tiles; the small and fp32 shapes trade list
     // space for a co-resident CTA / weight chunks
     static constexpr int MAX_UNITS = (SPLIT || TILES <= 2 || CIN < 64) ? TC_MAX_UNITS_SPLIT : TC_MAX_UNITS;
-    static constexpr int WARPS = RING ? PW + 3 : PW + 2;     // producers | MMA issuer | weight loader | (map streamer)
+    static constexpr int WARPS = RING ? PW + 3 : PW + NP + 1; // producers | MMA issuer(s) | weight loader | (map streamer)
     static constexpr int THREADS = WARPS * 32;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * BST + 1 + (RING ? 2 * TC_IDX_RING : 0);
     // one ring entry: 128 map entries per tap of the group; with several taps per entry each tap's 512 bytes are followed
@@ -78,7 +85,7 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static constexpr int SUB_STRIDE = G > 1 ? 528 : 512;
     static constexpr int RING_BYTES = G * SUB_STRIDE;
     static constexpr size_t SMEM = 1024 + size_t(STAGES) * TC_A_BYTES + size_t(BST) * B_BYTES + size_t(RING ? TC_IDX_RING : 0) * RING_BYTES +
-                                   size_t(MAX_UNITS) * 2 + 8 * NUM_BARS + 16;
+                                   size_t(MAX_UNITS) * 2 * (MODE == 3 ? 2 : 1) + 8 * NUM_BARS + 16;
     // co-resident CTAs: limited by TMEM columns (512 per SM) and shared memory (228 KB per SM, 1 KB reserved per CTA).
     // Three small CTAs per SM beat two larger ones by ~10 % on the 32- and 64-channel shapes: more independent
     // producer -> MMA -> commit chains hide the per-unit hand-off latency (profiles/r01_experiments.md)
@@ -88,11 +95,12 @@ template <int CIN, int COUT, int TILES, int STAGES, int BST, int PW, bool SPLIT 
     static_assert(CTAS_PER_SM >= 1, "configuration does not fit one SM");
     static_assert((CIN % 64 == 0 || CIN == 32 || CIN == 16) && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel counts");
     static_assert(TILES * ACC_COLS <= 512 && TILES <= 8 && KB <= 4, "accumulators exceed TMEM / unit encoding");
-    static_assert(MODE == 0 ? PW == 4 : (PW >= 2 && PW <= 4 && G == 1), "producer warps / mode");
+    static_assert(MODE == 0 ? PW == 4 : MODE == 3 ? (PW % 2 == 0 && PW >= 4 && PW <= 8 && G == 1 && !SPLIT) : (PW >= 2 && PW <= 4 && G == 1), "producer warps / mode");
+    static_assert(MODE != 3 || (STAGES % NP == 0 && SP >= 2 && TILES % NP == 0), "pipelines: two producer warps need two stages each");
     static_assert(WARPS >= 4, "the epilogue needs one warp per TMEM lane quarter");
     // warp-per-unit producers hold PW units in flight: with fewer stages a warp could meet a stage barrier two phases behind,
     // which a parity wait cannot tell from a ready one
-    static_assert(MODE == 0 || STAGES >= PW, "warp-per-unit producers need at least PW stages");
+    static_assert(MODE != 1 || STAGES >= PW, "warp-per-unit producers need at least PW stages");
 };
 
 __device__ __forceinline__ float load_any_f(const void *p, int64_t i, int dtype) {
@@ -203,14 +211,15 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     using Cfg = TcFwdCfg<CIN, COUT, TILES, STAGES, BST, PW, SPLIT, MODE>;
     constexpr int KB = Cfg::KB, G = Cfg::G, CPT = Cfg::CPT, THREADS = Cfg::THREADS, NS = Cfg::NS, XS = Cfg::XS, ACC = Cfg::ACC_COLS;
     constexpr bool RING = Cfg::RING;
-    constexpr int WARP_MMA = PW, WARP_B = PW + 1;
+    constexpr int NP = Cfg::NP, SP = Cfg::SP, TP = Cfg::TP, PCAP = Cfg::MAX_UNITS / NP;
+    constexpr int WARP_MMA = PW, WARP_B = PW + NP; // MMA issuers: warps PW .. PW + NP - 1
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + STAGES * TC_A_BYTES;
     const uint32_t smem_idx = smem_b + BST * Cfg::B_BYTES;
     const uint32_t smem_units = smem_idx + (RING ? TC_IDX_RING : 0) * Cfg::RING_BYTES;
-    const uint32_t bars = smem_units + Cfg::MAX_UNITS * 2;
+    const uint32_t bars = smem_units + Cfg::MAX_UNITS * 2 * (MODE == 3 ? 2 : 1);
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_bfull = bars + 16 * STAGES, bar_bempty = bar_bfull + 8 * BST;
     const uint32_t bar_accum = bar_bempty + 8 * BST;
@@ -219,6 +228,8 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
     uint16_t *units = reinterpret_cast<uint16_t *>(smem_gen + (smem_units - smem_base));
+    uint16_t *units_p = units + Cfg::MAX_UNITS; // MODE 3: pipeline p's own units, in order, at units_p + p * PCAP
+    __shared__ int s_np[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total_tiles = (n_out + TC_TILE_M - 1) / TC_TILE_M;
@@ -252,9 +263,9 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         }
         for (int b = 0; b < BST; ++b) {
             mbar_init(bar_bfull + 8 * b, 1); // expect_tx arrival + bytes
-            mbar_init(bar_bempty + 8 * b, 1);
+            mbar_init(bar_bempty + 8 * b, NP); // every pipeline releases every chunk
         }
-        mbar_init(bar_accum, 1);
+        mbar_init(bar_accum, NP);
         if (RING) {
             for (int e = 0; e < TC_IDX_RING; ++e) {
                 mbar_init(bar_ifull + 8 * e, 32);  // one completion-triggered arrival per streamer lane
@@ -301,6 +312,23 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int nunits = s_nunits;
+    if constexpr (MODE == 3) { // warp p < NP compacts pipeline p's units (tiles p TP .. p TP + TP - 1) out of the CTA's list, in order
+        if (warp < NP) {
+            int base = 0;
+            for (int u0 = 0; u0 < nunits; u0 += 32) {
+                const int u = u0 + lane;
+                const uint32_t unit = u < nunits ? units[u] : 0u;
+                const bool mine = u < nunits && int(unit & 7u) / TP == warp;
+                const uint32_t ballot = __ballot_sync(0xffffffffu, mine);
+                if (mine)
+                    units_p[warp * PCAP + base + __popc(ballot & ((1u << lane) - 1u))] = uint16_t(unit);
+                base += __popc(ballot);
+            }
+            if (lane == 0)
+                s_np[warp] = base;
+        }
+        __syncthreads();
+    }
 
     if (warp < PW) {
         if constexpr (!RING) {
@@ -312,23 +340,29 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             const uint32_t lane_off = (uint32_t(lg) << 12) | (uint32_t(q) << 4); // row 32 lg, chunk q; XOR with the per-i constant below
             const int32_t *lane_nbr = nbr + tile0 * TC_TILE_M + lane * 4;
             const int src_lane0 = 8 * lg;
+            // whose units: the CTA's (MODE 1: warp w takes u = w, w + PW, ...) or this warp's pipeline's (MODE 3: the two
+            // producer warps of pipeline p alternate over its list and fill its SP stages)
+            const uint16_t *ulist = MODE == 3 ? units_p + (warp >> 1) * PCAP : units;
+            const int n_own = MODE == 3 ? s_np[warp >> 1] : nunits;
+            const int first = MODE == 3 ? (warp & 1) : warp, stage0 = MODE == 3 ? (warp >> 1) * SP : 0;
+            constexpr int STRIDE = MODE == 3 ? 2 : PW;
             auto load_idx = [&](int uu) -> int4 {
-                if (uu >= nunits)
+                if (uu >= n_own)
                     return make_int4(-1, -1, -1, -1);
-                const uint32_t un = units[uu];
+                const uint32_t un = ulist[uu];
                 return __ldg(reinterpret_cast<const int4 *>(lane_nbr + int64_t(un >> 7) * pitch + int(un & 7) * TC_TILE_M));
             };
-            int4 pf0 = load_idx(warp), pf1 = load_idx(warp + PW);
-            for (int u = warp; u < nunits; u += PW) {
-                const uint32_t unit = units[u];
+            int4 pf0 = load_idx(first), pf1 = load_idx(first + STRIDE);
+            for (int u = first; u < n_own; u += STRIDE) {
+                const uint32_t unit = ulist[u];
                 const int j = (unit >> 5) & 3, t = unit & 7;
                 const int4 cur = pf0;
                 pf0 = pf1;
-                pf1 = load_idx(u + 2 * PW);
-                const int s = u % STAGES;
+                pf1 = load_idx(u + 2 * STRIDE);
+                const int s = stage0 + u % SP;
                 const int64_t rows_left = n_out - (tile0 + t) * TC_TILE_M - 32 * lg; // row i + 32 lg exists iff i < rows_left
                 const uint16_t *xj = x + q * 8 + j * 64 + (SPLIT ? int((unit >> 3) & 3u) * CIN : 0);
-                mbar_wait(bar_empty + 8 * s, ((u / STAGES) & 1) ^ 1u);
+                mbar_wait(bar_empty + 8 * s, ((u / SP) & 1) ^ 1u);
                 const uint32_t dst = smem_a + s * TC_A_BYTES;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -405,14 +439,16 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             }
             cp_async_wait_all();
         }
-    } else if (warp == WARP_MMA) {
-        // ================= MMA issuer (one thread) =================
+    } else if (warp >= WARP_MMA && warp < WARP_MMA + NP) {
+        // ================= MMA issuer of pipeline p (one thread): walks the CTA's unit list, issues its own tiles' units,
+        //                   and takes part in every weight chunk's hand-shake (a chunk is free once ALL pipelines are past it) =====
         if (lane == 0) {
+            const int p = warp - WARP_MMA;
             // descriptor = {hi: SBO 1024 | version 1 | SWIZZLE_128B, lo: (addr >> 4) | LBO 16 B}; only lo changes
             const uint64_t desc_hi = make_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | (1u << 16);
-            int s = 0, c = -1, prev_kj = -1;
-            uint32_t ph = 0, started = 0, started_small = 0, b_lo = 0;
+            int own = 0, c = -1, prev_kj = -1; // own: units of this pipeline issued so far
+            uint32_t started = 0, started_small = 0, b_lo = 0;
             for (int u = 0; u < nunits; ++u) {
                 const uint32_t unit = units[u];
                 const int kj = int(unit >> 5), t = unit & 7;
@@ -424,6 +460,11 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                     b_lo = b_lo0 + uint32_t(c % BST) * (Cfg::B_BYTES >> 4);
                     prev_kj = kj;
                 }
+                if (NP > 1 && t / TP != p)
+                    continue; // another pipeline's tile
+                const int s = p * SP + own % SP;
+                const uint32_t ph = uint32_t(own / SP) & 1u;
+                ++own;
                 mbar_wait(bar_full + 8 * s, ph);
                 // the gathered rows were written through the generic proxy (cp.async); tcgen05.mma reads shared memory
                 // through the async proxy: order the two before the first MMA of the stage
@@ -455,10 +496,6 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 }
                 umma_commit(bar_empty + 8 * s); // stage reusable once these MMAs retire
                 started |= 1u << t;
-                if (++s == STAGES) {
-                    s = 0;
-                    ph ^= 1u;
-                }
             }
             umma_commit(bar_accum);
         }
@@ -793,8 +830,10 @@ static inline TcShape tc_shape(int32_t cin, int32_t cout, bool split) {
     case 16: return wide ? TcShape{8, 4, 2, 4, 1} : TcShape{8, 3, 2, 4, 0};
     case 32: return wide ? TcShape{4, 4, 2, 4, 1} : TcShape{4, 3, 2, 4, 0};
     case 64: return wide ? TcShape{2, 2, 2, 2, 1} : TcShape{2, 3, 2, 4, 0};
-    case 128: return wide ? TcShape{2, 4, 2, 3, 1} : TcShape{1, 2, 2, 4, 0};
-    default: return TcShape{2, 6, 3, 4, 0};
+    // 128- and 256-wide outputs: two pipelines (a tile, two producer warps and an MMA warp each) share the weight chunks, which
+    // are 48 % / 64 % of these shapes' L2 -> SM traffic (128 -> 128: 0.817 -> 0.757 ms, 256 -> 256: 2.67 -> 2.40 ms on the C2 batch)
+    case 128: return wide ? TcShape{2, 4, 2, 4, 3} : TcShape{1, 2, 2, 4, 0};
+    default: return wide ? TcShape{2, 4, 2, 4, 3} : TcShape{2, 6, 3, 4, 0};
     }
 }
 
@@ -873,6 +912,8 @@ static int tc_forward_split(const ConvArgs &a, const void *x, const uint8_t *img
 static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img) {
     if (takes_ts(a.cin, a.cout, a.k3, a.dtype))
         return tc_ts_forward(a, x, img);
+    if (g_tc_variant == 15 && a.cin == 256 && a.cout == 256 && !a.epi.stats)
+        return launch_tc_fwd<256, 256, 2, 6, 3, 4, false, 0>(a, x, img); // the round-1 shape of the 256-wide outputs (A/B baseline)
     // experiment knob (fvc_set_tuning(0, v), scripts/bench_variants.py): alternative pipeline shapes of the two headline shapes
     if (g_tc_variant != 0 && a.cin == a.cout && (a.cin == 64 || a.cin == 128) && !a.epi.stats) { // (statistics blocks follow the default shape)
         const bool c64 = a.cin == 64;
@@ -885,6 +926,8 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
         case 7: return c64 ? launch_tc_fwd<64, 64, 2, 3, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 1, 2, 1, 2, false, 1>(a, x, img); // 3 CTAs / SM (64), 4 (128)
         case 8: return c64 ? launch_tc_fwd<64, 64, 1, 2, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 3, 2, 2, false, 1>(a, x, img);
         case 9: return c64 ? launch_tc_fwd<64, 64, 2, 3, 2, 2, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 4, 6, 2, 3, false, 1>(a, x, img);
+        case 13: return c64 ? launch_tc_fwd<64, 64, 4, 4, 3, 4, false, 3>(a, x, img) : launch_tc_fwd<128, 128, 2, 4, 2, 3, false, 1>(a, x, img); // 64: 2 pipelines, 2 CTAs / SM; 128: the single-pipeline shape
+        case 14: return c64 ? launch_tc_fwd<64, 64, 8, 8, 3, 8, false, 3>(a, x, img) : launch_tc_fwd<128, 128, 4, 8, 3, 8, false, 3>(a, x, img); // 4 pipelines, 1 CTA / SM
         case 10: return c64 ? launch_tc_fwd<64, 64, 4, 3, 2, 3, false, 1>(a, x, img) : launch_tc_fwd<128, 128, 2, 3, 2, 3, false, 1>(a, x, img);
         default: break;
         }
@@ -915,8 +958,8 @@ static int tc_forward_half(const ConvArgs &a, const void *x, const uint8_t *img)
     FVC_TC_LAUNCH(CI, 16, 8, 4, 2, 4, false, 1) \
     FVC_TC_LAUNCH(CI, 32, 4, 4, 2, 4, false, 1) \
     FVC_TC_LAUNCH(CI, 64, 2, 2, 2, 2, false, 1) \
-    FVC_TC_LAUNCH(CI, 128, 2, 4, 2, 3, false, 1) \
-    FVC_TC_LAUNCH(CI, 256, 2, 6, 3, 4, false, 0)
+    FVC_TC_LAUNCH(CI, 128, 2, 4, 2, 4, false, 3) \
+    FVC_TC_LAUNCH(CI, 256, 2, 4, 2, 4, false, 3)
     FVC_TC_NARROW(16)
     FVC_TC_NARROW(32)
     FVC_TC_WIDE(64)

@@ -30,6 +30,8 @@ int g_wgrad_variant = 0;
 constexpr int WG_PW = 4;                  // gather-producer warps (also the epilogue warps)
 constexpr int WG_WARP_MMA = WG_PW;        // warp WG_PW + 1 streams the kernel map
 constexpr int WG_THREADS = (WG_PW + 2) * 32;
+constexpr int WG_THREADS_PIPE = (WG_PW + 3) * 32; // MODE 1: producers | two MMA warps | dY loader
+constexpr int wg_threads(int mode) { return mode == 1 ? WG_THREADS_PIPE : WG_THREADS; }
 constexpr int WG_TILE = 128;
 constexpr int WG_BLOCK_BYTES = WG_TILE * 128; // 128 rows x 64 reduction-side elements x 2 B
 
@@ -82,8 +84,16 @@ __device__ __forceinline__ void lds_v4x2(uint32_t addr, int (&v)[8]) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr + 16) : "memory");
 }
 
-template <int CIN, int COUT, int STAGES, bool SPLIT, int CTAS, int BSTG>
-__global__ void __launch_bounds__(WG_THREADS, CTAS)
+// MODE 0: the four producer warps share every unit (a quarter of its rows each), a streamer warp feeds them map entries through
+//         a shared-memory ring (round 1; still serves fp32, whose per-segment drain keeps the producers in step with the issuer).
+// MODE 1: two pipelines per CTA (half precision).  Pipeline p owns the units (accumulators) ul = p (mod 2), STAGES / 2 gather
+//         stages, two producer warps -- warp (p, h) gathers WHOLE 16 KB blocks, block h of each of the pipeline's units: 32 x
+//         16-byte cp.async per lane, map entries by eight 16-byte loads one block ahead, no ring -- and its OWN MMA-issuing warp;
+//         a seventh warp loads the dY tiles both pipelines read.  One issuing thread per SM needs ~850-1200 dependent cycles per
+//         unit (uniform-register moves, mbarrier round trips: profiles/r02_ts_executor.md) and was what the wide shapes, which
+//         run one CTA per SM, waited for.
+template <int CIN, int COUT, int STAGES, bool SPLIT, int CTAS, int BSTG, int MODE>
+__global__ void __launch_bounds__(wg_threads(MODE), CTAS)
 conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
                      int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
                      int tiles_per_chunk, int seg_tiles, uint32_t idesc, float *__restrict__ partial) {
@@ -149,14 +159,14 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     if (threadIdx.x == 0) {
         s_started[0] = s_started[1] = 0u;
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, WG_PW * 32);
+            mbar_init(bar_full + 8 * s, MODE == 1 ? 64 : WG_PW * 32); // MODE 1: the two warps that gather a unit's two blocks
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_bfull + 8 * b, WG_PW * 32);
-            mbar_init(bar_bempty + 8 * b, 1);
+            mbar_init(bar_bfull + 8 * b, MODE == 1 ? 32 : WG_PW * 32); // MODE 1: the dY loader warp
+            mbar_init(bar_bempty + 8 * b, MODE == 1 ? 2 : 1); // MODE 1: both pipelines release a dY tile
         }
-        mbar_init(bar_accum, 1);
+        mbar_init(bar_accum, MODE == 1 ? 2 : 1);
         for (int e = 0; e < RING; ++e) {
             mbar_init(bar_ifull + 8 * e, 32);
             mbar_init(bar_iempty + 8 * e, WG_PW);
@@ -180,64 +190,9 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         const int half = warp >> 1;
         const int kk = (warp & 1) * 32 + lane;
         float *slice = partial + int64_t(blockIdx.x) * k3 * CIN * COUT;
-        int s = 0, e = 0, tb = 0, seg = 0, seg_t = 0;
-        uint32_t ph = 0, eph = 0;
-        for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
-            const int64_t rows_left = n_out - tile * WG_TILE - row0; // row row0 + i exists iff i < rows_left
-            const uint32_t live = live_units(tile);
-            { // B: plain rows of dY (identity "map"), every split; lanes beyond a narrow row's chunks zero-fill
-                const int bs = tb % BSTAGES;
-                mbar_wait(bar_bempty + 8 * bs, ((tb / BSTAGES) & 1) ^ 1);
-                int self[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    self[i] = (i < rows_left && q < Cfg::BQ) ? int(tile * WG_TILE + row0 + i) : -1;
-#pragma unroll
-                for (int j = 0; j < NS; ++j)
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb)
-                        gather_rows(smem_b + bs * Cfg::B_STAGE + (j * NB + nb) * WG_BLOCK_BYTES + dst0, q, dyq + j * COUT + nb * 64, YS, self);
-                cp_async_arrive_noinc(bar_bfull + 8 * bs);
-            }
-            for (uint32_t rest = live; rest; rest &= rest - 1u) {
-                const int blk = 2 * (unit0 + __ffs(rest) - 1);
-                const bool ok0 = first_tap(blk) + sub < k3;
-                const bool ok1 = blk + 1 < total_blocks && first_tap(blk + 1) + sub < k3; // odd block count: zero dummy
-                for (int i = 0; i < NS; ++i) {
-                    mbar_wait(bar_ifull + 8 * e, eph);
-                    int idx0[8], idx1[8];
-                    const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * Cfg::SUB_STRIDE + row0 * 4;
-                    lds_v4x2(entry, idx0);
-                    lds_v4x2(entry + G * Cfg::SUB_STRIDE, idx1);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        if (r >= rows_left || !ok0)
-                            idx0[r] = -1;
-                        if (r >= rows_left || !ok1)
-                            idx1[r] = -1;
-                    }
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                    const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
-                    gather_rows(stage, q, xq + i * CIN + (CIN >= 64 ? (blk % CB) * 64 : 0), XS, idx0);
-                    gather_rows(stage + WG_BLOCK_BYTES, q, xq + i * CIN + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), XS, idx1);
-                    __syncwarp();
-                    if (lane == 0)
-                        mbar_arrive(bar_iempty + 8 * e);
-                    cp_async_arrive_noinc(bar_full + 8 * s);
-                    if (++s == STAGES) {
-                        s = 0;
-                        ph ^= 1u;
-                    }
-                    if (++e == RING) {
-                        e = 0;
-                        eph ^= 1u;
-                    }
-                }
-            }
-            if (++seg_t < seg_tiles && tile + 1 < tile_end)
-                continue;
-            // ---- drain: accumulators -> fp32 partial slice [k][ci][co] (first segment stores, later ones add).  The issuer
-            //      cannot touch TMEM again before every producer thread has arrived on the next stage, i.e. after this.
+        // ---- drain: accumulators -> fp32 partial slice [k][ci][co] (first segment stores, later ones add).  The issuer
+        //      cannot touch TMEM again before every producer thread has arrived on the next stage, i.e. after this.
+        auto drain = [&](int seg) {
             mbar_wait(bar_accum, uint32_t(seg & 1));
             tc_fence_after();
             const uint32_t started = *reinterpret_cast<volatile uint32_t *>(&s_started[seg & 1]);
@@ -294,12 +249,191 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     }
                 }
             }
+        };
+        if constexpr (MODE == 1) {
+            // ================= MODE 1 producers: warp (p, h) gathers block h of every unit of pipeline p =================
+            // lane = (lg, q): 8 lanes q cover one 128-byte row; lane group lg owns the 32 consecutive rows 32 lg .. 32 lg + 31 and
+            // copies 16-byte chunk q of each.  Its 32 map entries (tap `sub` of the block) are eight 16-byte loads, one block ahead.
+            static_assert(!SPLIT && STAGES % 2 == 0, "pipelines: half precision, an even number of gather stages");
+            constexpr int SPW = STAGES / 2; // stages per pipeline
+            const int p = warp >> 1, h = warp & 1;
+            const uint32_t pmask = p ? 0xAAAAAAAAu : 0x55555555u; // units ul = p (mod 2)
+            const int lg = lane >> 3;
+            const uint32_t lane_off = (uint32_t(lg) << 12) | (uint32_t(q) << 4);
+            struct Item {
+                int64_t tile;
+                int blk, stage, use;
+            };
+            int64_t e_tile = tile_begin - 1;
+            uint32_t e_rest = 0u;
+            int e_j = 0; // units of this pipeline so far
+            auto next_item = [&](Item &out) -> bool { // (tile ascending, own live unit ascending): the order the pipeline's MMA warp walks
+                while (true) {
+                    if (e_rest == 0u) {
+                        if (e_tile + 1 >= tile_end)
+                            return false;
+                        ++e_tile;
+                        e_rest = live_units(e_tile) & pmask;
+                        continue;
+                    }
+                    out.tile = e_tile;
+                    out.blk = 2 * (unit0 + __ffs(e_rest) - 1) + h;
+                    out.stage = p * SPW + e_j % SPW;
+                    out.use = e_j / SPW;
+                    e_rest &= e_rest - 1u;
+                    ++e_j;
+                    return true;
+                }
+            };
+            auto load_idx = [&](const Item &item, int4 (&out)[8]) {
+                const int tap = first_tap(item.blk) + sub;
+                if (item.blk < total_blocks && tap < k3) { // (an odd block count leaves a zero dummy block in the last unit)
+                    const int4 *src = reinterpret_cast<const int4 *>(nbr + int64_t(tap) * pitch + item.tile * WG_TILE + lg * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        out[j] = __ldg(src + j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        out[j] = make_int4(-1, -1, -1, -1);
+                }
+            };
+            Item cur, fut;
+            int4 idx[8], nxt[8];
+            bool have = next_item(cur);
+            if (have)
+                load_idx(cur, idx);
+            while (have) {
+                const bool have_next = next_item(fut);
+                if (have_next)
+                    load_idx(fut, nxt);
+                const int64_t rows_left = n_out - cur.tile * WG_TILE - lg * 32; // row 32 lg + i exists iff i < rows_left
+                const uint16_t *src0 = xq + (CIN >= 64 ? (cur.blk % CB) * 64 : 0);
+                mbar_wait(bar_empty + 8 * cur.stage, (cur.use & 1) ^ 1u);
+                const uint32_t dst = smem_a + cur.stage * Cfg::A_STAGE + (cur.blk & 1) * WG_BLOCK_BYTES;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int v[4] = {idx[j].x, idx[j].y, idx[j].z, idx[j].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int i = 4 * j + c;
+                        const bool ok = v[c] >= 0 && i < rows_left;
+                        cp_async16(dst + (lane_off ^ uint32_t(i * 128 + ((i & 7) << 4))), ok ? src0 + int64_t(v[c]) * XS : x, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(bar_full + 8 * cur.stage);
+                cur = fut;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    idx[j] = nxt[j];
+                have = have_next;
+            }
+            cp_async_wait_all();
+            drain(0); // half precision: one segment, drained once every tile of the chunk has been accumulated
+            tc_fence_before();
+        } else {
+        int s = 0, e = 0, tb = 0, seg = 0, seg_t = 0;
+        uint32_t ph = 0, eph = 0;
+        for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+            const int64_t rows_left = n_out - tile * WG_TILE - row0; // row row0 + i exists iff i < rows_left
+            const uint32_t live = live_units(tile);
+            { // B: plain rows of dY (identity "map"), every split; lanes beyond a narrow row's chunks zero-fill
+                const int bs = tb % BSTAGES;
+                mbar_wait(bar_bempty + 8 * bs, ((tb / BSTAGES) & 1) ^ 1);
+                int self[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    self[i] = (i < rows_left && q < Cfg::BQ) ? int(tile * WG_TILE + row0 + i) : -1;
+#pragma unroll
+                for (int j = 0; j < NS; ++j)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+                        gather_rows(smem_b + bs * Cfg::B_STAGE + (j * NB + nb) * WG_BLOCK_BYTES + dst0, q, dyq + j * COUT + nb * 64, YS, self);
+                cp_async_arrive_noinc(bar_bfull + 8 * bs);
+            }
+            for (uint32_t rest = live; rest; rest &= rest - 1u) {
+                const int blk = 2 * (unit0 + __ffs(rest) - 1);
+                const bool ok0 = first_tap(blk) + sub < k3;
+                const bool ok1 = blk + 1 < total_blocks && first_tap(blk + 1) + sub < k3; // odd block count: zero dummy
+                for (int i = 0; i < NS; ++i) {
+                    mbar_wait(bar_ifull + 8 * e, eph);
+                    int idx0[8], idx1[8];
+                    const uint32_t entry = smem_idx + e * Cfg::RING_BYTES + sub * Cfg::SUB_STRIDE + row0 * 4;
+                    lds_v4x2(entry, idx0);
+                    lds_v4x2(entry + G * Cfg::SUB_STRIDE, idx1);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (r >= rows_left || !ok0)
+                            idx0[r] = -1;
+                        if (r >= rows_left || !ok1)
+                            idx1[r] = -1;
+                    }
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const uint32_t stage = smem_a + s * Cfg::A_STAGE + dst0;
+                    gather_rows(stage, q, xq + i * CIN + (CIN >= 64 ? (blk % CB) * 64 : 0), XS, idx0);
+                    gather_rows(stage + WG_BLOCK_BYTES, q, xq + i * CIN + (CIN >= 64 ? ((blk + 1) % CB) * 64 : 0), XS, idx1);
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(bar_iempty + 8 * e);
+                    cp_async_arrive_noinc(bar_full + 8 * s);
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                    if (++e == RING) {
+                        e = 0;
+                        eph ^= 1u;
+                    }
+                }
+            }
+            if (++seg_t < seg_tiles && tile + 1 < tile_end)
+                continue;
+            drain(seg);
             tc_fence_before();
             ++seg;
             seg_t = 0;
         }
         cp_async_wait_all();
-    } else if (warp == WG_WARP_MMA) {
+        } // MODE 0
+    } else if (MODE == 1 && (warp == WG_WARP_MMA || warp == WG_WARP_MMA + 1)) {
+        // ================= MODE 1: MMA issuer of pipeline p (its own units, its own stages; the dY tile is shared) =================
+        if (lane == 0) {
+            constexpr int SPW = STAGES / 2;
+            const int p = warp - WG_WARP_MMA;
+            const uint32_t pmask = p ? 0xAAAAAAAAu : 0x55555555u;
+            const uint64_t desc_hi = make_smem_desc_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFF00000000ull;
+            const uint32_t lbo = uint32_t(WG_BLOCK_BYTES >> 4) << 16;
+            const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | lbo;
+            int j = 0, tb = 0;
+            uint32_t started = 0;
+            for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+                const int bs = tb % BSTAGES;
+                const uint32_t live = live_units(tile) & pmask;
+                mbar_wait(bar_bfull + 8 * bs, (tb / BSTAGES) & 1); // both pipelines take part in every tile's dY hand-shake
+                fence_proxy_async();
+                const uint32_t b_lo = b_lo0 + uint32_t(bs) * (Cfg::B_STAGE >> 4);
+                for (uint32_t rest = live; rest; rest &= rest - 1u, ++j) {
+                    const int ul = __ffs(rest) - 1;
+                    const int s = p * SPW + j % SPW;
+                    mbar_wait(bar_full + 8 * s, (j / SPW) & 1);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + uint32_t(s) * (Cfg::A_STAGE >> 4);
+                    const uint32_t acc0 = (started >> ul) & 1u;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_f16(tmem_base + uint32_t(ul * ACC), desc_hi | (a_lo + 128 * kk), desc_hi | (b_lo + 128 * kk), idesc, acc0 | uint32_t(kk != 0));
+                    started |= 1u << ul;
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_bempty + 8 * bs);
+            }
+            atomicOr(&s_started[0], started); // the two pipelines' accumulators are disjoint: the drain reads the union
+            __threadfence_block();
+            umma_commit(bar_accum);
+        }
+        __syncwarp();
+    } else if (MODE != 1 && warp == WG_WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
             // MN-major SWIZZLE_128B descriptors: LBO = distance between the two 64-wide blocks, SBO = 8-row group
@@ -353,6 +487,28 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             }
         }
         __syncwarp();
+    } else if constexpr (MODE == 1) {
+        // ================= dY tile loader (whole warp, the seventh): 128 plain rows per tile, every 64-channel block =================
+        const int q = lane & 7, lg = lane >> 3;
+        const uint32_t lane_off = (uint32_t(lg) << 12) | (uint32_t(q) << 4);
+        const uint16_t *dyq = dy + q * 8;
+        int tb = 0;
+        for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+            const int bs = tb % BSTAGES;
+            const int64_t row0 = tile * WG_TILE + lg * 32;
+            mbar_wait(bar_bempty + 8 * bs, ((tb / BSTAGES) & 1) ^ 1);
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const uint32_t dst = smem_b + bs * Cfg::B_STAGE + nb * WG_BLOCK_BYTES;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const bool ok = row0 + i < n_out && q < Cfg::BQ; // lanes beyond a narrow row's chunks zero-fill
+                    cp_async16(dst + (lane_off ^ uint32_t(i * 128 + ((i & 7) << 4))), ok ? dyq + (row0 + i) * YS + nb * 64 : dy, ok ? 16u : 0u);
+                }
+            }
+            cp_async_arrive_noinc(bar_bfull + 8 * bs);
+        }
+        cp_async_wait_all();
     } else {
         // ================= kernel-map streamer (whole warp): every tap of both blocks of each live unit =================
         int e = 0;
@@ -425,10 +581,10 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split
 
 // tc_split_rows (conv_tc.cu) writes the bf16 split rows of an fp32 operand
 
-template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1, int BSTG = 0>
+template <int CIN, int COUT, int STAGES, bool SPLIT = false, int CTAS = 1, int BSTG = 0, int MODE = 0>
 static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, float *partial) {
     using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS, BSTG>;
-    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT, CTAS, BSTG>;
+    auto kernel = conv_tc_wgrad_kernel<CIN, COUT, STAGES, SPLIT, CTAS, BSTG, MODE>;
     const int ctas_planned = wgrad_ctas(CIN, COUT, SPLIT);
     FVC_REQUIRE(CTAS == ctas_planned, FVC_ERR_RUNTIME, "weight-gradient plan / kernel shape mismatch");
     static std::atomic<unsigned long long> configured{0}; // per instantiation, one bit per device
@@ -438,7 +594,7 @@ static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, fl
     const WgradPlan p = plan_wgrad(a.n_out, CIN, COUT, a.k3, SPLIT);
     const uint32_t idesc = make_idesc_f16(128, Cfg::NPAD, SPLIT || a.dtype == FVC_BF16, true, true);
     dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
-    kernel<<<grid, WG_THREADS, Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<const uint16_t *>(dy), a.nbr,
+    kernel<<<grid, wg_threads(MODE), Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<const uint16_t *>(dy), a.nbr,
                                                       a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out, a.k3,
                                                       p.units_per_group, p.tiles_per_chunk, p.seg_tiles, idesc, partial);
     FVC_LAUNCH_CHECK();
@@ -519,23 +675,42 @@ int tc_wgrad(const WgradArgs &a) {
         return launch_tc_wgrad<64, 64, 2, false, 2, 1>(a, a.x, a.dy, partial); // round-1 shape: one dY buffer
     if (g_wgrad_variant == 2 && a.cin == 64 && a.cout == 64)
         return launch_tc_wgrad<64, 64, 4, false, 1, 2>(a, a.x, a.dy, partial);
+    // two pipelines per CTA (MODE 1) are the default of the 128- / 256-wide outputs (one CTA per SM: 128 -> 128 1.348 -> 1.265 ms,
+    // 256 -> 256 4.60 -> 4.51 ms on the C2 batch); on 64 -> 64, which runs two CTAs per SM, they lose (0.562 -> 0.591 ms): knob only
+    if (g_wgrad_variant == 3 && a.cin == 64 && a.cout == 64)
+        return launch_tc_wgrad<64, 64, 2, false, 2, 0, 1>(a, a.x, a.dy, partial);
+    if (g_wgrad_variant == 3 && a.cin == 128 && a.cout == 128)
+        return launch_tc_wgrad<128, 128, 4>(a, a.x, a.dy, partial); // the single-pipeline shape (A/B baseline)
+    if (g_wgrad_variant == 3 && a.cin == 256 && a.cout == 256)
+        return launch_tc_wgrad<256, 256, 2>(a, a.x, a.dy, partial);
 #define FVC_WG_CASE(CI, CO, S)       \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S>(a, a.x, a.dy, partial);
 #define FVC_WG_CASE2(CI, CO, S)      \
     if (a.cin == CI && a.cout == CO) \
         return launch_tc_wgrad<CI, CO, S, false, 2>(a, a.x, a.dy, partial);
+#define FVC_WG_CASEP(CI, CO, S)      \
+    if (a.cin == CI && a.cout == CO) \
+        return launch_tc_wgrad<CI, CO, S, false, 1, 0, 1>(a, a.x, a.dy, partial);
 #define FVC_WG_CIN(CI)       \
     FVC_WG_CASE2(CI, 16, 2)  \
     FVC_WG_CASE2(CI, 32, 2)  \
     FVC_WG_CASE2(CI, 64, 2)  \
     FVC_WG_CASE(CI, 128, 4)  \
     FVC_WG_CASE(CI, 256, 2)
+#define FVC_WG_CIN_WIDE(CI)  \
+    FVC_WG_CASE2(CI, 16, 2)  \
+    FVC_WG_CASE2(CI, 32, 2)  \
+    FVC_WG_CASE2(CI, 64, 2)  \
+    FVC_WG_CASEP(CI, 128, 4) \
+    FVC_WG_CASEP(CI, 256, 2)
     FVC_WG_CIN(16)
     FVC_WG_CIN(32)
-    FVC_WG_CIN(64)
-    FVC_WG_CIN(128)
-    FVC_WG_CIN(256)
+    FVC_WG_CIN_WIDE(64)
+    FVC_WG_CIN_WIDE(128)
+    FVC_WG_CIN_WIDE(256)
+#undef FVC_WG_CIN_WIDE
+#undef FVC_WG_CASEP
 #undef FVC_WG_CIN
 #undef FVC_WG_CASE
 #undef FVC_WG_CASE2

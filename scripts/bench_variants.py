@@ -58,10 +58,10 @@ if len(sys.argv) > 3:
     with open(sys.argv[3], "w") as fh:
         json.dump(rows, fh, indent=1)
 # weight-gradient shapes (key 1) on the same batch
-if cin == cout == 64:
+if cin == cout and cin in (64, 128, 256):
     dy = torch.randn((n, cout), device=dev).to(dtype)
     wrows, wref = [], None
-    for variant in (0, 1, 2):
+    for variant in ((0, 1, 2, 3) if cin == 64 else (0, 3)):  # 3 = two pipelines (64) / the single-pipeline baseline (128, 256)
         cpp.set_kernel_variant(variant, wgrad=True)
         f = lambda: cpp.gs_conv_backward(dy, x, w, topo, need_grad_features=False)[1]  # noqa: E731
         gw = f()

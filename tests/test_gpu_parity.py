@@ -430,7 +430,7 @@ def test_conv_bn_act_block_matches_the_separate_modules(fvdb, dtype, cin, cout, 
     assert _rel_err(fused, chain.cpu()) <= tol
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 13, 14])
 @pytest.mark.parametrize("channels", [64, 128])
 def test_forward_pipeline_variants_agree_with_oracle(fvdb, variant, channels):
     # the bench knob's pipeline shapes (warp-per-unit producers with 2 / 3 / 4 warps, 1..3 CTAs per SM, and the round-1 ring kernel)
