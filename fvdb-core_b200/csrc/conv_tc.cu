@@ -816,8 +816,15 @@ static inline bool tc_channels_ok(int32_t c, int32_t max_c) { return (c == 16 ||
 struct TcShape {
     int tiles, stages, bst, pw, mode;
 };
-static inline TcShape tc_shape(int32_t cin, int32_t cout, bool split) {
+// Small fp32 batches (BASELINE.json configs[0]: 100 k voxels = 782 tiles) do not fill the machine with the multi-tile CTAs of
+// the table -- 196 four-tile CTAs walk 168 units each, one after the other -- so they run 1-tile CTAs, three per SM.
+static inline bool tc_small_batch(int64_t n_out, int32_t cin, int32_t cout, bool split) {
+    return split && cin < 64 && cout <= 64 && ceil_div(n_out > 0 ? n_out : 1, TC_TILE_M) <= 4096;
+}
+static inline TcShape tc_shape(int32_t cin, int32_t cout, bool split, bool small = false) {
     const bool wide = cin >= 64;
+    if (small)
+        return TcShape{1, 2, 2, 4, 0};
     if (split) {
         switch (cout) {
         case 16: return wide ? TcShape{8, 4, 3, 4, 1} : TcShape{8, 4, 3, 4, 0};
@@ -857,7 +864,7 @@ static inline bool takes_ts(int32_t cin, int32_t cout, int64_t k3, int32_t dtype
 int64_t tc_stats_blocks(int64_t n_out, int32_t cin, int32_t cout, int64_t k3, int32_t dtype, int32_t *rows_per_block) {
     if (takes_ts(cin, cout, k3, dtype))
         return tc_ts_stats_blocks(n_out, rows_per_block);
-    const int tiles = tc_shape(cin, cout, dtype == FVC_F32).tiles;
+    const int tiles = tc_shape(cin, cout, dtype == FVC_F32, tc_small_batch(n_out, cin, cout, dtype == FVC_F32)).tiles;
     if (rows_per_block)
         *rows_per_block = tiles * TC_TILE_M;
     return ceil_div(ceil_div(n_out > 0 ? n_out : 0, TC_TILE_M), tiles);
@@ -889,6 +896,18 @@ int tc_split_rows(const float *x, int64_t n, int c, uint16_t *xs, cudaStream_t s
     }
 
 static int tc_forward_split(const ConvArgs &a, const void *x, const uint8_t *img) {
+    if (tc_small_batch(a.n_out, a.cin, a.cout, true)) {
+#define FVC_TCS_SMALL(CI, CO)          \
+    if (a.cin == CI && a.cout == CO) \
+        return launch_tc_fwd<CI, CO, 1, 2, 2, 4, true, 0>(a, x, img);
+        FVC_TCS_SMALL(16, 16)
+        FVC_TCS_SMALL(16, 32)
+        FVC_TCS_SMALL(16, 64)
+        FVC_TCS_SMALL(32, 16)
+        FVC_TCS_SMALL(32, 32)
+        FVC_TCS_SMALL(32, 64)
+#undef FVC_TCS_SMALL
+    }
 #define FVC_TCS_NARROW(CI)                    \
     FVC_TC_LAUNCH(CI, 16, 8, 4, 3, 4, true, 0) \
     FVC_TC_LAUNCH(CI, 32, 4, 4, 3, 4, true, 0) \
