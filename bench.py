@@ -948,6 +948,7 @@ def main():
     ap.add_argument("--sync-bn", action="store_true", help="c3: batch statistics over all ranks (fvdb.nn.SyncBatchNorm)")
     ap.add_argument("--grids", type=int, default=0, help="override the number of grids per GPU (experiments)")
     ap.add_argument("--variant", type=int, default=0, help="experiments: pipeline-shape variant of the tensor-core forward kernel (fvc_set_tuning)")
+    ap.add_argument("--wgrad-variant", type=int, default=0, help="experiments: variant of the weight-gradient kernel (fvc_set_tuning key 1)")
     ap.add_argument("--c4-grids", type=int, default=0, help="override the number of grids of the strong_c4 sub-record (experiments)")
     args = ap.parse_args()
     config_name = args.config or "c2"
@@ -959,6 +960,10 @@ def main():
         from fvdb import _fvdb_cpp
 
         _fvdb_cpp.set_kernel_variant(args.variant)
+    if args.wgrad_variant and args.impl == "ours":
+        from fvdb import _fvdb_cpp
+
+        _fvdb_cpp.set_kernel_variant(args.wgrad_variant, wgrad=True)
     if args.impl == "reference":
         run_reference(args, cfg)
     elif config_name == "c3":

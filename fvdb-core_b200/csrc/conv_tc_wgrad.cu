@@ -96,7 +96,7 @@ template <int CIN, int COUT, int STAGES, bool SPLIT, int CTAS, int BSTG, int MOD
 __global__ void __launch_bounds__(wg_threads(MODE), CTAS)
 conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ dy, const int32_t *__restrict__ nbr,
                      int64_t pitch, const unsigned long long *__restrict__ tile_mask, int64_t n_out, int k3, int units_per_group,
-                     int tiles_per_chunk, int seg_tiles, uint32_t idesc, float *__restrict__ partial) {
+                     int tiles_per_chunk, int mini, int seg_tiles, uint32_t idesc, float *__restrict__ partial) {
     using Cfg = TcWgradCfg<CIN, COUT, STAGES, SPLIT, CTAS, BSTG>;
     constexpr int G = Cfg::G, CB = Cfg::CB, CPT = Cfg::CPT, NB = Cfg::NB, NPAD = Cfg::NPAD, RING = Cfg::RING;
     constexpr int NS = Cfg::NS, XS = Cfg::XS, YS = Cfg::YS, ACC = Cfg::ACC_COLS, BSTAGES = Cfg::BSTAGES;
@@ -122,8 +122,20 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
     const int unit0 = blockIdx.y * units_per_group;
     const int nunits = total_units - unit0 < units_per_group ? total_units - unit0 : units_per_group;
     const int64_t total_tiles = (n_out + WG_TILE - 1) / WG_TILE;
+    // This CTA's tiles, q = 0 .. n_my - 1.  mini > 0: mini-chunks of `mini` consecutive tiles dealt round-robin over the gridDim.x
+    // row chunks, so that ALL resident CTAs -- every row chunk and every tap group -- sweep the tile space together and what
+    // they touch at one time (dY tiles re-read by each tap group, feature rows re-gathered by neighbouring taps) stays in L2;
+    // with one contiguous range per CTA (mini == 0, round 1) the tap groups of a chunk drift apart and the ranges of the
+    // chunks are far apart to begin with: the 128 -> 128 weight gradient read 3.6 GB from DRAM for 0.9 GB of operands.
     const int64_t tile_begin = int64_t(blockIdx.x) * tiles_per_chunk;
     const int64_t tile_end = tile_begin + tiles_per_chunk < total_tiles ? tile_begin + tiles_per_chunk : total_tiles;
+    int64_t n_my = tile_end - tile_begin;
+    if (mini > 0) {
+        const int64_t mcs = (total_tiles + mini - 1) / mini, x = blockIdx.x, X = gridDim.x;
+        const int64_t mine = mcs > x ? (mcs - 1 - x) / X + 1 : 0;
+        n_my = mine * mini - ((mine > 0 && (mcs - 1) % X == x) ? mcs * mini - total_tiles : 0); // (the last mini-chunk may be short)
+    }
+    auto tile_of = [&](int64_t q) -> int64_t { return mini > 0 ? ((q / mini) * gridDim.x + blockIdx.x) * mini + q % mini : tile_begin + q; };
     auto first_tap = [&](int blk) -> int { return CIN >= 64 ? blk / CB : blk * G; };
 
     // (tile, unit) skipping: a unit is live for a tile iff one of its taps reaches a row of the tile.  Every role derives
@@ -264,15 +276,15 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                 int64_t tile;
                 int blk, stage, use;
             };
-            int64_t e_tile = tile_begin - 1;
+            int64_t e_q = -1, e_tile = 0;
             uint32_t e_rest = 0u;
             int e_j = 0; // units of this pipeline so far
             auto next_item = [&](Item &out) -> bool { // (tile ascending, own live unit ascending): the order the pipeline's MMA warp walks
                 while (true) {
                     if (e_rest == 0u) {
-                        if (e_tile + 1 >= tile_end)
+                        if (e_q + 1 >= n_my)
                             return false;
-                        ++e_tile;
+                        e_tile = tile_of(++e_q);
                         e_rest = live_units(e_tile) & pmask;
                         continue;
                     }
@@ -334,7 +346,8 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         } else {
         int s = 0, e = 0, tb = 0, seg = 0, seg_t = 0;
         uint32_t ph = 0, eph = 0;
-        for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+        for (int64_t qi = 0; qi < n_my; ++qi, ++tb) {
+            const int64_t tile = tile_of(qi);
             const int64_t rows_left = n_out - tile * WG_TILE - row0; // row row0 + i exists iff i < rows_left
             const uint32_t live = live_units(tile);
             { // B: plain rows of dY (identity "map"), every split; lanes beyond a narrow row's chunks zero-fill
@@ -386,7 +399,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     }
                 }
             }
-            if (++seg_t < seg_tiles && tile + 1 < tile_end)
+            if (++seg_t < seg_tiles && qi + 1 < n_my)
                 continue;
             drain(seg);
             tc_fence_before();
@@ -406,7 +419,8 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | lbo;
             int j = 0, tb = 0;
             uint32_t started = 0;
-            for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+            for (int64_t qi = 0; qi < n_my; ++qi, ++tb) {
+            const int64_t tile = tile_of(qi);
                 const int bs = tb % BSTAGES;
                 const uint32_t live = live_units(tile) & pmask;
                 mbar_wait(bar_bfull + 8 * bs, (tb / BSTAGES) & 1); // both pipelines take part in every tile's dY hand-shake
@@ -442,7 +456,8 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | lbo;
             int s = 0, tb = 0, seg = 0, seg_t = 0;
             uint32_t ph = 0, started = 0, started_small = 0;
-            for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+            for (int64_t qi = 0; qi < n_my; ++qi, ++tb) {
+            const int64_t tile = tile_of(qi);
                 const int bs = tb % BSTAGES;
                 const uint32_t live = live_units(tile);
                 mbar_wait(bar_bfull + 8 * bs, (tb / BSTAGES) & 1);
@@ -476,7 +491,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
                     }
                 }
                 umma_commit(bar_bempty + 8 * bs);
-                if (++seg_t == seg_tiles || tile + 1 == tile_end) { // segment done: hand the accumulators to the drain
+                if (++seg_t == seg_tiles || qi + 1 == n_my) { // segment done: hand the accumulators to the drain
                     *reinterpret_cast<volatile uint32_t *>(&s_started[seg & 1]) = started;
                     __threadfence_block();
                     umma_commit(bar_accum);
@@ -493,7 +508,8 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         const uint32_t lane_off = (uint32_t(lg) << 12) | (uint32_t(q) << 4);
         const uint16_t *dyq = dy + q * 8;
         int tb = 0;
-        for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++tb) {
+        for (int64_t qi = 0; qi < n_my; ++qi, ++tb) {
+            const int64_t tile = tile_of(qi);
             const int bs = tb % BSTAGES;
             const int64_t row0 = tile * WG_TILE + lg * 32;
             mbar_wait(bar_bempty + 8 * bs, ((tb / BSTAGES) & 1) ^ 1);
@@ -514,7 +530,8 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         int e = 0;
         uint32_t eph = 0;
         const int32_t *lane_nbr = nbr + lane * 4;
-        for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        for (int64_t qi = 0; qi < n_my; ++qi) {
+            const int64_t tile = tile_of(qi);
             const uint32_t live = live_units(tile);
             for (uint32_t rest = live; rest; rest &= rest - 1u) {
                 const int blk = 2 * (unit0 + __ffs(rest) - 1);
@@ -547,7 +564,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
 
 // ---- host side ------------------------------------------------------------------------------------
 struct WgradPlan {
-    int groups, units_per_group, chunks, tiles_per_chunk, seg_tiles;
+    int groups, units_per_group, chunks, tiles_per_chunk, mini, seg_tiles;
 };
 
 constexpr int WG_SPLIT_SEG_TILES = 32; // fp32: drain the accumulators every 32 row tiles (<= 256 full-magnitude MMA steps)
@@ -573,9 +590,15 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split
         chunks = 1;
     if (chunks > tiles)
         chunks = tiles;
+    // tiles per mini-chunk (see the kernel): 8 by default; knob: 5 = contiguous ranges (round 1), 6 / 7 / 8 = 16 / 32 / 64
+    p.mini = g_wgrad_variant == 5 ? 0 : g_wgrad_variant == 6 ? 16 : g_wgrad_variant == 7 ? 32 : g_wgrad_variant == 8 ? 64 : 8;
     p.tiles_per_chunk = int(ceil_div(tiles, chunks));
     p.chunks = int(ceil_div(tiles, p.tiles_per_chunk));
-    p.seg_tiles = split ? WG_SPLIT_SEG_TILES : p.tiles_per_chunk;
+    if (p.mini > 0) { // every CTA gets at least one mini-chunk
+        const int64_t mcs = ceil_div(tiles, p.mini);
+        p.chunks = int(chunks < mcs ? chunks : mcs);
+    }
+    p.seg_tiles = split ? WG_SPLIT_SEG_TILES : (1 << 30); // half precision: one segment, drained after the CTA's last tile
     return p;
 }
 
@@ -596,7 +619,7 @@ static int launch_tc_wgrad(const WgradArgs &a, const void *x, const void *dy, fl
     dim3 grid((unsigned)p.chunks, (unsigned)p.groups);
     kernel<<<grid, wg_threads(MODE), Cfg::SMEM, a.stream>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<const uint16_t *>(dy), a.nbr,
                                                       a.pitch, reinterpret_cast<const unsigned long long *>(a.tile_mask), a.n_out, a.k3,
-                                                      p.units_per_group, p.tiles_per_chunk, p.seg_tiles, idesc, partial);
+                                                      p.units_per_group, p.tiles_per_chunk, p.mini, p.seg_tiles, idesc, partial);
     FVC_LAUNCH_CHECK();
     return wgrad_reduce_partials(partial, p.chunks, a.cin, a.cout, a.k3, a.dtype, a.grad_w, a.stream);
 }

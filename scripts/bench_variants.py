@@ -61,7 +61,8 @@ if len(sys.argv) > 3:
 if cin == cout and cin in (64, 128, 256):
     dy = torch.randn((n, cout), device=dev).to(dtype)
     wrows, wref = [], None
-    for variant in ((0, 1, 2, 3) if cin == 64 else (0, 3)):  # 3 = two pipelines (64) / the single-pipeline baseline (128, 256)
+    # 3 = two pipelines (64) / the single-pipeline baseline (128, 256); 5 = contiguous tile ranges per CTA, 6 / 7 / 8 = mini-chunks of 8 / 32 / 64 tiles
+    for variant in ((0, 1, 2, 3, 5, 6, 7, 8) if cin == 64 else (0, 3, 5, 6, 7, 8)):
         cpp.set_kernel_variant(variant, wgrad=True)
         f = lambda: cpp.gs_conv_backward(dy, x, w, topo, need_grad_features=False)[1]  # noqa: E731
         gw = f()
@@ -76,7 +77,8 @@ if cin == cout and cin in (64, 128, 256):
             f()
         b.record()
         torch.cuda.synchronize()
-        wrows.append({"wgrad_variant": variant, "wgrad_ms": a.elapsed_time(b) / 10, "max_abs_diff_vs_first": float((gw.float() - wref.float()).abs().max())})
+        wrows.append({"wgrad_variant": variant, "wgrad_ms": a.elapsed_time(b) / 10, "max_abs_diff_vs_first": float((gw.float() - wref.float()).abs().max()),
+                      "max_abs": float(wref.float().abs().max())})
         print(json.dumps(wrows[-1]), flush=True)
     cpp.set_kernel_variant(0, wgrad=True)
     if len(sys.argv) > 3:
