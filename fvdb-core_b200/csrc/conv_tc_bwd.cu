@@ -506,7 +506,7 @@ template <int CG, int CX> static int launch_bwd_fused(const BwdFusedArgs &a) {
     const uint32_t idesc1 = make_idesc_f16(128, CX, bf16, false, false), idesc2 = make_idesc_f16(128, CX, bf16, true, true);
     float *partial = reinterpret_cast<float *>(a.scratch);
     static int *report = nullptr; // debug runs only: a host-mapped slot the kernel names a timed-out wait in
-    const bool debug = getenv("FVC_DEBUG_WAITS") != nullptr;
+    static const bool debug = getenv("FVC_DEBUG_WAITS") != nullptr; // read once per process
     if (debug && !report && cudaHostAlloc(reinterpret_cast<void **>(&report), 64, cudaHostAllocMapped) != cudaSuccess)
         report = nullptr;
     if (debug && report)
