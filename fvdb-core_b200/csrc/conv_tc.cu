@@ -443,12 +443,12 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
         // ================= MMA issuer of pipeline p (one thread): walks the CTA's unit list, issues its own tiles' units,
         //                   and takes part in every weight chunk's hand-shake (a chunk is free once ALL pipelines are past it) =====
         if (lane == 0) {
-            const int p = warp - WARP_MMA;
+            const int p = NP > 1 ? warp - WARP_MMA : 0; // (a compile-time 0 for the single-pipeline shapes: nothing extra on their issuing thread)
             // descriptor = {hi: SBO 1024 | version 1 | SWIZZLE_128B, lo: (addr >> 4) | LBO 16 B}; only lo changes
             const uint64_t desc_hi = make_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | (1u << 16);
-            int own = 0, c = -1, prev_kj = -1; // own: units of this pipeline issued so far
-            uint32_t started = 0, started_small = 0, b_lo = 0;
+            int sl = 0, c = -1, prev_kj = -1; // sl: this pipeline's next stage (of its SP), ph: its phase
+            uint32_t ph = 0, started = 0, started_small = 0, b_lo = 0;
             for (int u = 0; u < nunits; ++u) {
                 const uint32_t unit = units[u];
                 const int kj = int(unit >> 5), t = unit & 7;
@@ -462,9 +462,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 }
                 if (NP > 1 && t / TP != p)
                     continue; // another pipeline's tile
-                const int s = p * SP + own % SP;
-                const uint32_t ph = uint32_t(own / SP) & 1u;
-                ++own;
+                const int s = p * SP + sl;
                 mbar_wait(bar_full + 8 * s, ph);
                 // the gathered rows were written through the generic proxy (cp.async); tcgen05.mma reads shared memory
                 // through the async proxy: order the two before the first MMA of the stage
@@ -496,6 +494,10 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
                 }
                 umma_commit(bar_empty + 8 * s); // stage reusable once these MMAs retire
                 started |= 1u << t;
+                if (++sl == SP) { // (counters, not own % SP: a division on the issuing thread is time every unit waits for)
+                    sl = 0;
+                    ph ^= 1u;
+                }
             }
             umma_commit(bar_accum);
         }

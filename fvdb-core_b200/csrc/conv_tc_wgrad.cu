@@ -593,6 +593,8 @@ static WgradPlan plan_wgrad(int64_t n_out, int cin, int cout, int k3, bool split
     // tiles per mini-chunk (see the kernel): 8 by default; knob: 5 = contiguous ranges (round 1), 6 / 7 / 8 = 16 / 32 / 64
     p.mini = g_wgrad_variant == 5 ? 0 : g_wgrad_variant == 6 ? 16 : g_wgrad_variant == 7 ? 32 : g_wgrad_variant == 8 ? 64 : 8;
     p.tiles_per_chunk = int(ceil_div(tiles, chunks));
+    if (p.mini > 0 && p.tiles_per_chunk < 4 * p.mini) // small batches: keep at least ~4 mini-chunks per CTA, or the deal is uneven
+        p.mini = p.tiles_per_chunk >= 4 ? p.tiles_per_chunk / 4 : 1;
     p.chunks = int(ceil_div(tiles, p.tiles_per_chunk));
     if (p.mini > 0) { // every CTA gets at least one mini-chunk
         const int64_t mcs = ceil_div(tiles, p.mini);
