@@ -5,7 +5,7 @@ Exports the names the reference's convolution users import from ``fvdb``: ``Grid
 low-level ``_fvdb_cpp`` module.  Importing fails loudly if libfvdbconv.so has not been built.
 """
 
-from . import _fvdb_cpp, nn, torch_jagged
+from . import _fvdb_cpp, nn
 from .convolution_plan import ConvolutionCoverageReport, ConvolutionCoverageWarning, ConvolutionPlan, ConvolutionTransformCompatibility
 from .enums import ConvolutionPhasePolicy, ConvolutionTopologyPolicy, ConvolutionTopologyProvenance
 from .grid_batch import GridBatch
@@ -24,6 +24,5 @@ __all__ = [
     "ConvolutionTopologyPolicy",
     "ConvolutionTopologyProvenance",
     "nn",
-    "torch_jagged",
     "_fvdb_cpp",
 ]

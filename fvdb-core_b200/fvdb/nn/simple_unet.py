@@ -4,7 +4,7 @@ Same class names, constructor arguments, sub-module attribute names (``state_dic
 and data flow: pad (conv onto the dilated grid) -> recursive down / up levels (max-pool, 1x1x1 fan-out, residual blocks,
 1x1x1 fan-in, nearest refinement, additive skip) -> unpad (transposed conv back onto the input grid).  Every convolution
 goes through ``ConvolutionPlan``; BatchNorm + ReLU pairs run as one fused pass (csrc/norm.cu) -- the same function as the
-reference's separate ``BatchNorm`` then ``torch_jagged.relu``.
+reference's separate ``BatchNorm`` then ``fvdb.torch_jagged.relu``.
 """
 
 from __future__ import annotations
@@ -12,7 +12,6 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .. import torch_jagged
 from ..convolution_plan import ConvolutionPlan
 from ..grid_batch import GridBatch
 from ..jagged_tensor import JaggedTensor
@@ -69,7 +68,8 @@ class SimpleUNetConvBlock(nn.Module):
         residual = data
         for block in self.blocks:
             data = block(data, plan)
-        return torch_jagged.relu(data + residual)
+        out = data + residual
+        return out.jagged_like(torch.relu(out.jdata))
 
 
 class SimpleUNetDown(nn.Module):
