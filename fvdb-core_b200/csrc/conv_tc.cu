@@ -442,7 +442,7 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
     } else if (warp >= WARP_MMA && warp < WARP_MMA + NP) {
         // ================= MMA issuer of pipeline p (one thread): walks the CTA's unit list, issues its own tiles' units,
         //                   and takes part in every weight chunk's hand-shake (a chunk is free once ALL pipelines are past it) =====
-        if (lane == 0) {
+        if (elect_one()) { // (not `lane == 0`: see tc_ptx.cuh)
             const int p = NP > 1 ? warp - WARP_MMA : 0; // (a compile-time 0 for the single-pipeline shapes: nothing extra on their issuing thread)
             // descriptor = {hi: SBO 1024 | version 1 | SWIZZLE_128B, lo: (addr >> 4) | LBO 16 B}; only lo changes
             const uint64_t desc_hi = make_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;

@@ -365,7 +365,7 @@ conv_tc_bwd_fused_kernel(const uint16_t *__restrict__ dy, const uint16_t *__rest
         cp_async_wait_all();
     } else if (warp == BF_WARP_MMA) {
         // ================= MMA issuer (one thread): resident W^T image, then per live unit MMA1 x 8 + MMA2 x 8 =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t w_bytes = uint32_t(total_blocks) * Cfg::WCHUNK;
             mbar_expect_tx(bar_w, w_bytes);
             for (uint32_t off = 0; off < w_bytes; off += 32768u) // bulk copies of at most 32 KB

@@ -394,7 +394,7 @@ conv_tc_ts_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w_
     } else {
         // ================= MMA issuer of pipeline g (one thread): resident weight image, A from tensor memory =================
         const int g = warp - TS_WARP_MMA0;
-        if (lane == 0) {
+        if (elect_one()) {
             if (g == 0) {
                 const uint32_t w_bytes = uint32_t(total_blocks) * Cfg::WCHUNK;
                 mbar_expect_tx(bar_w, w_bytes);

@@ -410,7 +410,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         } // MODE 0
     } else if (MODE == 1 && (warp == WG_WARP_MMA || warp == WG_WARP_MMA + 1)) {
         // ================= MODE 1: MMA issuer of pipeline p (its own units, its own stages; the dY tile is shared) =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr int SPW = STAGES / 2;
             const int p = warp - WG_WARP_MMA;
             const uint32_t pmask = p ? 0xAAAAAAAAu : 0x55555555u;
@@ -449,7 +449,7 @@ conv_tc_wgrad_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict_
         __syncwarp();
     } else if (MODE != 1 && warp == WG_WARP_MMA) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             // MN-major SWIZZLE_128B descriptors: LBO = distance between the two 64-wide blocks, SBO = 8-row group
             const uint64_t desc_hi = make_smem_desc_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFF00000000ull;
             const uint32_t lbo = uint32_t(WG_BLOCK_BYTES >> 4) << 16;

@@ -106,6 +106,21 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // make generic-proxy shared-memory writes (cp.async / st.shared) visible to the async proxy (tcgen05.mma)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a fully active warp (elect.sync).  Code that issues tcgen05 instructions from a single thread should enter its
+// single-thread region through this, not through `lane == 0`: the compiler then KNOWS one lane is active and moves operands
+// to uniform registers directly instead of wrapping every tcgen05.mma / commit in an election loop (ELECT ... BRA.U.ANY).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0u;
+}
+
 // ---- tcgen05 --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -31,9 +31,10 @@ def set_conv_path(name: str) -> None:
     _path = _FORCED_PATH[name]
 
 
-# measured (profiles/r02_time_fused.jsonl): the fused kernel ties or loses against the two separate kernels on 4 of 5 narrow shapes (its
-# single persistent CTA per SM is bound by shared-memory bandwidth: one write + two MMA reads of every gathered block), so it is opt-in
-_fused_backward = os.environ.get("FVC_FUSED_BACKWARD", "0") == "1"
+# Narrow half-precision layers (16 / 32 channels): grad_features AND grad_weights from one gather of grad_output.  Measured
+# (profiles/r02_time_fused.jsonl, second block): 13 - 38 % faster than the two separate kernels on four of five narrow shapes and
+# a tie on the fifth, once its MMA-issuing thread entered through elect.sync; FVC_FUSED_BACKWARD=0 restores the separate kernels.
+_fused_backward = os.environ.get("FVC_FUSED_BACKWARD", "1") != "0"
 
 
 def set_fused_backward(enabled: bool) -> None:
