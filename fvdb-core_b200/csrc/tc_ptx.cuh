@@ -76,13 +76,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
-// TMA row gather (sm_100): four rows r0..r3 of a 2-D tensor map (box = {width, 1}) starting at column `col` land as four
-// consecutive box rows at `dst`, swizzled as the map says; out-of-range rows are zero-filled; bytes counted on `bar`
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
-                 "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
-                 : "memory");
-}
 // 16-byte LDGSTS; src_bytes = 0 zero-fills (a missing neighbour row)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
