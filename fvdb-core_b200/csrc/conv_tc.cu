@@ -449,8 +449,10 @@ conv_tc_fwd_kernel(const uint16_t *__restrict__ x, const uint8_t *__restrict__ w
             const uint32_t a_lo0 = ((smem_a & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_b & 0x3FFFFu) >> 4) | (1u << 16);
             int sl = 0, c = -1, prev_kj = -1; // sl: this pipeline's next stage (of its SP), ph: its phase
             uint32_t ph = 0, started = 0, started_small = 0, b_lo = 0;
+            uint32_t next_unit = nunits > 0 ? units[0] : 0u;
             for (int u = 0; u < nunits; ++u) {
-                const uint32_t unit = units[u];
+                const uint32_t unit = next_unit;
+                next_unit = units[u + 1 < nunits ? u + 1 : u]; // (one entry ahead: its shared-memory latency is off this thread's per-unit chain)
                 const int kj = int(unit >> 5), t = unit & 7;
                 if (kj != prev_kj) { // next weight stage
                     if (c >= 0)
