@@ -480,6 +480,8 @@ def conv_workload(D: Dist, cfg: dict, args, *, want_e2e: bool, want_gpu_baseline
     ms = start.elapsed_time(stop) / steps
     fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in phase_ms["fwd"]]))
     bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in phase_ms["dgrad+wgrad"]]))
+    # per-step device times (median and min next to the mean the contract's ms_per_step is)
+    per_step = [f[0].elapsed_time(b[1]) for f, b in zip(phase_ms["fwd"], phase_ms["dgrad+wgrad"])]
 
     # the three hot kernels, each timed alone on the launching stream (weights prepared outside the loop, as a layer would cache them)
     w_fwd = cpp._prepare_weights(w, dtype, False)
@@ -500,6 +502,7 @@ def conv_workload(D: Dist, cfg: dict, args, *, want_e2e: bool, want_gpu_baseline
 
     res = {"ms": ms, "n": n, "P": P, "k3": k3, "grids": grid.grid_count, "plan_ms": plan_ms, "launches": launches, "clocks": clocks.summary(),
            "per_kernel": per_kernel, "roof_ms": roof_ms, "comp_ms": comp_ms, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "peaks": peaks, "elem": s,
+           "step_median_ms": float(np.median(per_step)), "step_min_ms": float(np.min(per_step)),
            "gpu_baseline_ms": None, "e2e": None}
     if want_gpu_baseline:
         try:
@@ -630,6 +633,7 @@ def conv_record(D: Dist, cfg: dict, res: dict, *, steps: int, warmup: int, stron
         "roofline_step": {"roofline_ms": res["roof_ms"], "compulsory_ms": res["comp_ms"], "measured_ms": measured, "frac": res["roof_ms"] / measured,
                           "compulsory_frac": res["comp_ms"] / measured},
         "phase_ms": {"fwd": mx[2], "dgrad+wgrad": mx[3]},
+        "step_ms": {"mean": ms, "median": res["step_median_ms"], "min": res["step_min_ms"], "note": "this rank's per-step CUDA-event times; ms_per_step is the mean over the timed region, max over ranks"},
         "gpu_launches": int(res["launches"]), "clocks": res["clocks"],
     }
     if res.get("gpu_baseline_ms"):
