@@ -274,6 +274,29 @@ def test_bench_partition_by_grid_is_a_disjoint_cover():
     assert abs(loads[0] - loads[1]) <= max(int(c.shape[0]) for c in whole)  # LPT: imbalance bounded by one grid
 
 
+def test_bench_rooflines_credit_the_fused_backward_with_the_passes_it_replaces():
+    # the step roofline is the sum of the per-pass gathered bytes, whether the backward runs as two
+    # kernels or as the one fused kernel of the narrow layers; the compulsory floor never exceeds the gathered-bytes figure.
+    if str(REPO) not in sys.path:
+        sys.path.insert(0, str(REPO))
+    import bench
+
+    P, n, cin, cout, k3, s = 1_000_000_000, 40_000_000, 16, 16, 125, 2
+    peaks = {"hbm_gbs": 6546.9, "tflops": 1346.6, "source": "test"}
+    ab = bench.algorithmic_bytes(P, n, n, cin, cout, k3, s)
+    assert ab["fwd"] == P * cin * s + n * cout * s + 4 * P + k3 * cin * cout * s
+    assert ab["wgrad"] == P * (cin + cout) * s + 8 * P + 4 * k3 * cin * cout
+    assert ab["bwd_fused"] == ab["dgrad"] + ab["wgrad"]
+    assert bench.fused_formulation_bytes(P, n, n, cin, cout, k3, s) < ab["bwd_fused"]
+    separate, roof_sep, comp_sep = bench.kernel_rooflines({"fwd": 13.5, "dgrad": 13.5, "wgrad": 16.8}, P, n, n, cin, cout, k3, s, peaks)
+    fused, roof_fused, comp_fused = bench.kernel_rooflines({"fwd": 13.5, "dgrad": 13.5, "wgrad": 16.8, "bwd_fused": 24.0}, P, n, n, cin, cout, k3, s, peaks)
+    assert abs(roof_sep - roof_fused) < 1e-9  # same algorithm, same step roofline
+    assert comp_fused <= comp_sep and comp_sep < roof_sep
+    assert fused["bwd_fused"]["flops"] == 2 * fused["dgrad"]["flops"] and "fused_formulation_bytes" in fused["bwd_fused"]
+    for rec in fused.values():
+        assert 0.0 < rec["compulsory"]["frac"] <= rec["frac"] * 1.0000001
+
+
 def test_header_is_plain_c():
     # The drop-in boundary is a C ABI: include/fvdbconv.h must compile as C11 (no torch / C++ types in the signatures).
     import shutil
