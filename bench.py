@@ -465,6 +465,11 @@ def conv_workload(D: Dist, cfg: dict, args, *, want_e2e: bool, want_gpu_baseline
             phase_ms["dgrad+wgrad"].append((e1, e2))
         return y, gx, gw
 
+    if world > 1:  # untimed set-up: NCCL builds its channels lazily on the first collectives of a given size
+        probe = torch.zeros_like(w)
+        for _ in range(8):
+            dist.all_reduce(probe)
+        torch.cuda.synchronize()
     for _ in range(warmup):
         step(False)
     D.barrier()
